@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — patches/sec (128^3) of sliding-window inference on synthetic 384x384x160 volumes.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A step = the sliding-window inference of ONE synthetic volume (BASELINE.json configs[3]:
+384x384x160, 128^3 window, overlap 0.25, gaussian blending -> 32 patches) including the finalise
+kernel (probabilities, argmax mask, Dice sums).  N>1 (torchrun): the 32 windows of every volume are
+sharded by patch index over the ranks and the un-normalised accumulator is reduced to rank 0 with
+one NCCL reduce (strong scaling of a fixed volume).  One JSON line is printed by rank 0.
+
+--impl reference times the CPU oracle (restatement of the reference's torch/MONAI path; the
+reference itself cannot be imported on the GPU box) on the host cores, one patch per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOLUME = (384, 384, 160)
+ROI = (128, 128, 128)
+METRIC = "patches/sec (128^3) sliding-window infer"
+N_ROT = 4  # rotating volume buffers: 4 x (94 MB in + 189 MB acc) >> 126 MB L2
+
+
+def synth_volume(i, shape=VOLUME):
+    """N(0,1) noise + bright ellipsoid 'tumour', whole-volume normalised; label = mask."""
+    g = torch.Generator().manual_seed(1000 + i)
+    x = torch.randn(shape, generator=g)
+    c = [(0.25 + 0.5 * torch.rand(1, generator=g).item()) * s for s in shape]
+    xs = torch.arange(shape[0]).view(-1, 1, 1).float()
+    ys = torch.arange(shape[1]).view(1, -1, 1).float()
+    zs = torch.arange(shape[2]).view(1, 1, -1).float()
+    m = (((xs - c[0]) / 14) ** 2 + ((ys - c[1]) / 14) ** 2 + ((zs - c[2]) / 8) ** 2) <= 1
+    x = x + 2.0 * m.float()
+    x = (x - x.mean()) / x.std()
+    return x[None, None].contiguous(), m.float()[None, None].contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [v for v in sm if v > 0.5 * (mx or 1)] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_net(device):
+    from oracle.unet_oracle import (CHANNELS, KERNEL_SIZES, SAMPLE_KERNEL_SIZES, STRIDES, seeded_state_dict)
+    from params.networks.nets.unet2d5_spvPA import UNet2d5_spvPA
+    sd = seeded_state_dict(0)  # random-init weights of the reference architecture (no checkpoints offline)
+    net = UNet2d5_spvPA(dimensions=3, in_channels=1, out_channels=2, channels=CHANNELS, strides=STRIDES,
+                        kernel_sizes=KERNEL_SIZES, sample_kernel_sizes=SAMPLE_KERNEL_SIZES, num_res_units=2,
+                        norm="BATCH", dropout=0.1)
+    net.load_state_dict(sd)
+    return net.to(device).eval(), sd
+
+
+def cpu_oracle_patches(sd, vol, max_patches, budget_s):
+    """Times the CPU oracle (torch fp32, all host threads) on the first windows of `vol`."""
+    from oracle import sw_oracle, unet_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    starts = sw_oracle.window_starts(VOLUME, ROI, sw_oracle.scan_interval(VOLUME, ROI, 0.25))
+    outs, t_total, n = [], 0.0, 0
+    with torch.no_grad():
+        for j, s in enumerate(starts[: max_patches + 1]):
+            w = vol[:, :, s[0]:s[0] + ROI[0], s[1]:s[1] + ROI[1], s[2]:s[2] + ROI[2]]
+            t0 = time.perf_counter()
+            y = unet_oracle.unet_forward(sd, w)[0]
+            dt = time.perf_counter() - t0
+            outs.append((s, y))
+            if j > 0:  # first patch is the warm-up
+                t_total += dt
+                n += 1
+            if t_total > budget_s:
+                break
+    return outs, n, t_total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.unet_oracle import seeded_state_dict
+    sd = seeded_state_dict(0)
+    vol, _ = synth_volume(0)
+    from oracle import sw_oracle, unet_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    starts = sw_oracle.window_starts(VOLUME, ROI, sw_oracle.scan_interval(VOLUME, ROI, 0.25))
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            s = starts[i % len(starts)]
+            w = vol[:, :, s[0]:s[0] + ROI[0], s[1]:s[1] + ROI[1], s[2]:s[2] + ROI[2]]
+            t0 = time.perf_counter()
+            unet_oracle.unet_forward(sd, w)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    val = len(times) / total
+    sample = f"{len(times)} patches (128^3) of synthetic volume 0, 1 patch per step, sw_batch_size=1"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "VS_inference sliding-window 384x384x160, 128^3 window (configs[3])",
+                   "volume": list(VOLUME), "roi": list(ROI), "overlap": 0.25, "blend": "gaussian"},
+        "cpu_baseline": {"value": val, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from vs_seg_b200 import lib as vlib
+    from vs_seg_b200 import sliding_window as sw
+    from vs_seg_b200.tensors import f32view
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    vlib.load()
+    net, sd = build_net(dev)
+    predictor = lambda t: net(t)[0]  # noqa: E731
+    predictor.native_model = net
+    shard = (rank, world) if world > 1 else None
+
+    host = [synth_volume(i) for i in range(N_ROT)]
+    pinned = [(v.pin_memory(), l.pin_memory()) for v, l in host]
+    vols = [(v.to(dev), l.to(dev)) for v, l in host]
+    n_win = len(sw.window_starts(VOLUME, ROI, 0.25))
+    mask_host = torch.empty((1, 1) + VOLUME, dtype=torch.uint8).pin_memory()
+    sums_host = torch.empty((1, 3), dtype=torch.float64).pin_memory()
+
+    def infer(vol, label):
+        acc, cnt, lows, img = sw.sliding_window_accumulate(vol, ROI, predictor, 0.25, "gaussian",
+                                                           window_shard=shard)
+        if world > 1:
+            dist.reduce(acc, dst=0)
+            if rank != 0:
+                return None
+        return sw.finalize(acc, cnt, lows, img, label=label, return_mask=True)
+
+    def step_resident(i):
+        v, l = vols[i % N_ROT]
+        return infer(v, l)
+
+    dv = [torch.empty_like(vols[0][0]) for _ in range(2)]
+    dl = [torch.empty_like(vols[0][1]) for _ in range(2)]
+
+    def step_e2e(i):
+        hv, hl = pinned[i % N_ROT]
+        v, l = dv[i % 2], dl[i % 2]
+        v.copy_(hv, non_blocking=True)
+        l.copy_(hl, non_blocking=True)
+        res = infer(v, l)
+        if res is not None:
+            _, mask, sums = res
+            mask_host.copy_(mask, non_blocking=True)
+            sums_host.copy_(sums, non_blocking=True)
+
+    def timed(fn, warmup, steps):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        l0 = vlib.launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), vlib.launches() - l0
+
+    with torch.no_grad():
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        ms, launches = timed(step_resident, max(args.warmup, 3), args.steps)
+        ms_e2e, _ = timed(step_e2e, 2, args.steps)
+        clk = clocks.stop() if rank == 0 else None
+
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+        value = n_win * args.steps / (ms * 1e-3)
+        e2e_value = n_win * args.steps / (ms_e2e * 1e-3)
+
+        # ---- per-kernel profile of one patch (outside the timed region) -> roofline of the top kernel
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        plan = net.eval_plan(ROI, batch=1, device=dev)
+        vol0 = vols[0][0]
+        acc = torch.zeros((1, 2) + VOLUME, device=dev)
+        imap = sw.importance_map(ROI, "gaussian", 0.125, dev)
+        prof = plan.profile(f32view(vol0, (0, 0, 0), ROI), f32view(acc, (0, 0, 0), ROI), imap.data_ptr())
+        patch_ms = sum(p[4] for p in prof)
+        top = max(prof, key=lambda p: p[4])
+        tensor_bound = top[2] / max(top[3], 1) > 210  # FLOP/B above the ridge
+        if tensor_bound:
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            achieved = top[2] / (top[4] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s"}
+        else:
+            peak = peaks.get("hbm_gbs", 6650.0)
+            achieved = top[3] / (top[4] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s"}
+        roof.update({"frac": roof["achieved"] / peak, "traffic": None, "kernel": top[0],
+                     "kernel_ms": top[4], "share_of_patch": top[4] / patch_ms,
+                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                     "useful_tflops_whole_patch": plan.total_flops() / (patch_ms * 1e-3) / 1e12})
+
+        # ---- CPU baseline (the oracle on the host cores) + parity of the native logits against it
+        cpu = None
+        parity = None
+        if not args.no_cpu_baseline:
+            outs, n, t = cpu_oracle_patches(sd, host[0][0], max_patches=8, budget_s=args.cpu_budget_s)
+            cpu = {"value": n / t, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{n} consecutive 128^3 windows of synthetic volume 0 after 1 warm-up window, "
+                             f"torch {torch.__version__} fp32, {os.cpu_count()} host cpus"}
+            err, flips, ties = 0.0, 0, 0
+            for s, y in outs:
+                got = plan.forward(vol0[:, :, s[0]:s[0] + ROI[0], s[1]:s[1] + ROI[1], s[2]:s[2] + ROI[2]].contiguous())[0].cpu()
+                err = max(err, (got - y).abs().max().item())
+                margin = (y[:, 1] - y[:, 0]).abs()
+                flips += ((got.argmax(1) != y.argmax(1)) & (margin > 1e-4)).sum().item()
+                ties += (margin <= 1e-4).sum().item()
+            parity = {"max_abs_err_logits": err, "argmax_flips_margin_gt_1e-4": flips, "near_ties_le_1e-4": ties,
+                      "windows_checked": len(outs), "tolerance": 1e-3}
+
+        in_bytes = host[0][0].numel() * 4 + host[0][1].numel() * 4
+        out_bytes = mask_host.numel() + sums_host.numel() * 8
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "VS_inference sliding-window 384x384x160, 128^3 window (configs[3])",
+                       "volume": list(VOLUME), "roi": list(ROI), "overlap": 0.25, "blend": "gaussian",
+                       "patches_per_step": n_win, "sw_batch_size": 1, "weights": "seeded random init",
+                       "l2_policy": f"{N_ROT} rotating volumes (283 MB each) > 126 MB L2",
+                       "parallelism": f"patch-index shard x{world}, 1 NCCL reduce/volume" if world > 1 else "1 GPU"},
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "patch_ms_profiled": patch_ms,
+        }))
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

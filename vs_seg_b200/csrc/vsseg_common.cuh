@@ -1,0 +1,75 @@
+// Shared device helpers for the vsseg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vsseg_b200.h"
+
+namespace vsseg {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define VSSEG_REQUIRE(cond, ...)                 \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::vsseg::set_error(__VA_ARGS__);     \
+            return VSSEG_EINVAL;                 \
+        }                                        \
+    } while (0)
+
+// ---- split-bf16 <-> fp32 ------------------------------------------------------------------
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) {
+    return __uint_as_float(bits16 << 16);
+}
+
+// 8 channels (one 16-byte group) of the hi and lo planes -> 8 floats
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&v)[8]) {
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+    const uint32_t ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+        v[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+    }
+}
+
+__device__ __forceinline__ void split1(float v, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    float r = v - __bfloat162float(h);
+    __nv_bfloat16 l = __float2bfloat16_rn(r);
+    hi = (uint32_t)__bfloat16_as_ushort(h);
+    lo = (uint32_t)__bfloat16_as_ushort(l);
+}
+
+__device__ __forceinline__ void pack8(const float (&v)[8], uint4& h, uint4& l) {
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t h0, l0, h1, l1;
+        split1(v[2 * i], h0, l0);
+        split1(v[2 * i + 1], h1, l1);
+        hh[i] = h0 | (h1 << 16);
+        ll[i] = l0 | (l1 << 16);
+    }
+    h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == 1) return 1.0f / (1.0f + expf(-v));
+    return v >= 0.f ? v : v * slope;
+}
+
+// element offset of (b, cg, x, y, z) group start in an act8 plane
+__device__ __forceinline__ int64_t act8_off(int64_t bstride, int X, int Y, int Z, int b, int cg, int x, int y, int z) {
+    return (int64_t)b * bstride + ((((int64_t)cg * X + x) * Y + y) * Z + z) * 8;
+}
+
+}  // namespace vsseg

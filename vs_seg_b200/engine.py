@@ -1,0 +1,404 @@
+"""Eval-mode execution plan of UNet2d5_spvPA on the native kernels.
+
+The plan is derived from a reference-format ``state_dict`` (the source of truth); folded /
+packed weights are caches.  It mirrors the recursion of the reference builder
+(/root/reference/params/networks/nets/unet2d5_spvPA.py:56-89) but executes it as a flat list
+of fused kernel launches through the C ABI:
+
+  * Conv -> BatchNorm(eval) -> Dropout(eval = identity) -> PReLU is ONE launch
+    (convolutions.py:148-156), BN and bias folded into a per-channel scale/shift;
+  * the ResidualUnit sum is applied in the last conv's epilogue (convolutions.py:252-255);
+  * torch.cat of the skip connection is free: encoder and upsample write disjoint channel
+    ranges of one act8 buffer (MONAI SkipConnection, unet2d5_spvPA.py:89);
+  * the attention gate x*(1+att) runs in place on that buffer (attentionblock.py:44-47);
+  * the top ResidualUnit (conv_only + 1x1x1 shortcut, both linear) is a single conv whose
+    centre tap absorbs the shortcut, and can blend straight into the sliding-window
+    accumulator (MONAI sliding_window_inference step 6).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as _lib
+from .tensors import Act8Buffer, f32view
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def pack_conv_weight(w: torch.Tensor, transposed: bool, cout_pad: int | None = None) -> torch.Tensor:
+    """torch conv weight -> fp32 [taps][Cin][CoutPad] (tap = (tx*ky+ty)*kz+tz)."""
+    if transposed:  # ConvTranspose3d: [Cin, Cout, kx, ky, kz]
+        p = w.permute(2, 3, 4, 0, 1)
+    else:  # Conv3d: [Cout, Cin, kx, ky, kz]
+        p = w.permute(2, 3, 4, 1, 0)
+    kx, ky, kz, cin, cout = p.shape
+    p = p.reshape(kx * ky * kz, cin, cout).float()
+    if cout_pad is not None and cout_pad != cout:
+        p = torch.nn.functional.pad(p, (0, cout_pad - cout))
+    return p.contiguous()
+
+
+def fold_epilogue(sd, p, cout, cout_pad, norm: bool, act: str):
+    """Per-channel scale/shift of conv bias + eval BatchNorm3d (eps 1e-5), and the activation."""
+    bias = sd[p + "conv.bias"].double()
+    if norm:
+        g, b = sd[p + "norm.weight"].double(), sd[p + "norm.bias"].double()
+        m, v = sd[p + "norm.running_mean"].double(), sd[p + "norm.running_var"].double()
+        scale = g / torch.sqrt(v + 1e-5)
+        shift = b + (bias - m) * scale
+    else:
+        scale = torch.ones(cout, dtype=torch.float64, device=bias.device)
+        shift = bias
+    pad = (0, cout_pad - cout)
+    scale = torch.nn.functional.pad(scale.float(), pad, value=1.0)
+    shift = torch.nn.functional.pad(shift.float(), pad)
+    if act == "prelu":
+        slope, code = float(sd[p + "act.weight"].reshape(-1)[0]), 0
+    elif act == "relu":
+        slope, code = 0.0, 0
+    elif act == "none":
+        slope, code = 1.0, 0
+    elif act == "sigmoid":
+        slope, code = 0.0, 1
+    else:
+        raise ValueError(act)
+    return scale.contiguous(), shift.contiguous(), slope, code
+
+
+class _Step:
+    __slots__ = ("fn", "args", "name", "flops", "bytes", "kind")
+
+    def __init__(self, name, fn, args, flops=0, nbytes=0, kind="generic"):
+        self.name, self.fn, self.args = name, fn, args
+        self.flops, self.bytes, self.kind = int(flops), int(nbytes), kind
+
+
+def _nvox(v):
+    return v.B * v.X * v.Y * v.Z
+
+
+def _conv_cost(src, dst, k, transposed, cin, cout, extra_elems=0):
+    """Algorithmic cost of one conv launch: 2*MACs, and bytes = every activation element read once
+    and written once at 4 B (split-bf16 or fp32) plus fp32 weights."""
+    taps = k[0] * k[1] * k[2]
+    macs = (_nvox(src) if transposed else _nvox(dst)) * taps * cin * cout
+    nbytes = 4 * (_nvox(src) * cin + _nvox(dst) * cout + extra_elems + taps * cin * cout)
+    return 2 * macs, nbytes
+
+
+class UNetEvalPlan:
+    """Flat launch list for one patch shape [B,1,X,Y,Z] (X,Y % 32 == 0, Z % 8 == 0)."""
+
+    def __init__(self, state_dict, patch_size, batch=1, device="cuda:0", attention=True,
+                 channels=(16, 32, 48, 64, 80, 96),
+                 strides=((2, 2, 1), (2, 2, 1), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
+                 kernel_sizes=((3, 3, 1), (3, 3, 1), (3, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
+                 sample_kernel_sizes=((3, 3, 1), (3, 3, 1), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
+                 in_channels=1, out_channels=2):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.NativeLibraryError("UNetEvalPlan runs on a CUDA device only (no CPU fallback)")
+        if in_channels != 1 or out_channels not in (1, 2):
+            raise NotImplementedError("native plan supports in_channels=1, out_channels in {1,2}")
+        if channels[0] != 16 or any(c % 8 for c in channels):
+            raise NotImplementedError("native plan needs channels[0]==16 and channels % 8 == 0")
+        self.attention = bool(attention)
+        self.channels, self.strides = tuple(channels), tuple(tuple(s) for s in strides)
+        self.kernel_sizes = tuple(tuple(k) for k in kernel_sizes)
+        self.sample_kernel_sizes = tuple(tuple(k) for k in sample_kernel_sizes)
+        self.out_channels = out_channels
+        self.B = int(batch)
+        self.patch = tuple(int(v) for v in patch_size)
+        tot = [math.prod(s[d] for s in self.strides) for d in range(3)]
+        if any(self.patch[d] % tot[d] for d in range(3)):
+            raise ValueError(f"patch {self.patch} must be divisible by {tuple(tot)} "
+                             "(the reference's skip torch.cat fails otherwise)")
+        self.sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
+        self._keep = []  # device tensors referenced by raw pointers
+        self.steps = []
+        self.att_maps = []  # fp32 [B,1,x,y,z] tensors, coarsest first (hook order)
+        # the two per-call descriptors (mutated in place by run())
+        self.src = _lib.F32View()
+        self.dst = _lib.F32View()
+        self.sw_weight = C.c_void_p(None)
+        self._build()
+
+    # -- helpers ------------------------------------------------------------------------
+    def _dev(self, t):
+        t = t.to(self.device).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _geom(self, k, s=(1, 1, 1), transposed=False):
+        return _lib.ConvGeom(k[0], k[1], k[2], s[0], s[1], s[2], 1 if transposed else 0)
+
+    def _buf(self, C_, dims):
+        b = Act8Buffer(self.B, C_, dims[0], dims[1], dims[2], self.device)
+        self._keep.append(b)
+        return b
+
+    def _add_conv(self, name, p, src, dst, k, stride=(1, 1, 1), transposed=False, norm=True, act="prelu",
+                  res=None, res_cin1=None):
+        """src/dst: Act8 views.  One fused Convolution block (+ optional residual)."""
+        cout = dst.C
+        cpad = _round_up(cout, 16)
+        w = self._dev(pack_conv_weight(self.sd[p + "conv.weight"], transposed, cpad))
+        scale, shift, slope, code = fold_epilogue(self.sd, p, cout, cpad, norm, act)
+        scale, shift = self._dev(scale), self._dev(shift)
+        ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
+        g = self._geom(k, stride, transposed)
+        res_p = C.byref(res) if res is not None else None
+        if res_cin1 is not None:
+            rw, rb = res_cin1
+            args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep), None,
+                    C.byref(self.src), rw.data_ptr(), rb.data_ptr())
+        else:
+            args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep), res_p, None, None, None)
+        self._keep += [src, dst, g, ep, res]
+        extra = _nvox(dst) * cout if res is not None else (_nvox(dst) if res_cin1 is not None else 0)
+        fl, nb = _conv_cost(src, dst, k, transposed, src.C, cout, extra)
+        self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
+
+    def _add_shortcut(self, name, p, src, dst):
+        """1x1x1 shortcut conv of a ResidualUnit (convolutions.py:241-250) -> addend buffer."""
+        cout = dst.C
+        cpad = _round_up(cout, 16)
+        w = self._dev(pack_conv_weight(self.sd[p + "weight"], False, cpad))
+        scale = self._dev(torch.ones(cpad))
+        shift = self._dev(torch.nn.functional.pad(self.sd[p + "bias"].float(), (0, cpad - cout)))
+        ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), 1.0, 0)
+        g = self._geom((1, 1, 1))
+        args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep), None, None, None, None)
+        self._keep += [src, dst, g, ep]
+        fl, nb = _conv_cost(src, dst, (1, 1, 1), False, src.C, cout)
+        self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
+
+    def _add_att(self, name, p, buf, hid, k):
+        """AttentionBlock1+2 on act8 buffer `buf` (all channels), in place."""
+        cin = buf.C
+        src, h = buf.view(), hid.view(0, cin // 2)
+        self._add_conv(name + ".conv1", p + "0.conv1.", src, h, k, norm=False, act="relu")
+        att = torch.empty((self.B, 1, buf.X, buf.Y, buf.Z), dtype=torch.float32, device=self.device)
+        self.att_maps.append(att)
+        av = f32view(att)
+        w2 = self._dev(pack_conv_weight(self.sd[p + "0.conv2.conv.weight"], False))  # [taps][C/2][1]
+        b2 = self._dev(self.sd[p + "0.conv2.conv.bias"].float())
+        g = self._geom(k)
+        fl, nb = _conv_cost(h, av, k, False, h.C, 1)
+        self.steps.append(_Step(name + ".conv2", self.lib.vsseg_conv3d_smallcout,
+                                (C.byref(h), C.byref(av), C.byref(g), w2.data_ptr(), b2.data_ptr(), 1, 0.0, None),
+                                fl, nb))
+        self.steps.append(_Step(name + ".gate", self.lib.vsseg_att_gate, (C.byref(src), C.byref(av), C.byref(src)),
+                                2 * _nvox(src) * cin, 4 * _nvox(src) * (2 * cin + 1)))
+        self._keep += [src, h, av, g]
+
+    def _add_ru(self, name, p, src, h_buf, r_buf, dst, k, subunits):
+        """ResidualUnit with `subunits` Convolution blocks and a 1x1x1 shortcut; src/dst act8 views."""
+        cout = dst.C
+        r = r_buf.view(0, cout)
+        self._add_shortcut(name + ".residual", p + "residual.", src, r)
+        if subunits == 1:
+            self._add_conv(name + ".unit0", p + "conv.unit0.", src, dst, k, res=r)
+        else:
+            h = h_buf.view(0, cout)
+            self._add_conv(name + ".unit0", p + "conv.unit0.", src, h, k)
+            self._add_conv(name + ".unit1", p + "conv.unit1.", h, dst, k, res=r)
+
+    # -- plan ---------------------------------------------------------------------------
+    def _build(self):
+        ch, nlev = self.channels, len(self.channels)
+        dims = [self.patch]
+        for s in self.strides:
+            dims.append(tuple(d // q for d, q in zip(dims[-1], s)))
+        cat = [self._buf(2 * ch[l], dims[l]) for l in range(nlev - 1)]
+        hb = [self._buf(ch[l], dims[l]) for l in range(nlev - 1)]
+        rb = [self._buf(ch[l], dims[l]) for l in range(nlev - 1)]
+        dn = [self._buf(ch[l], dims[l + 1]) for l in range(nlev - 1)]
+        bot_h = self._buf(ch[-1], dims[-1])
+        bot_r = self._buf(ch[-1], dims[-1])
+        bot_o = self._buf(ch[-1], dims[-1])
+        bot_hid = self._buf(_round_up(ch[-2] // 2, 8), dims[-1])
+        self.buffers = dict(cat=cat, h=hb, r=rb, down=dn, bot_h=bot_h, bot_r=bot_r, bot_o=bot_o)
+
+        prefixes = []
+        p = "model."
+        for l in range(nlev - 1):
+            prefixes.append(p)
+            p = p + "1.submodule.1."
+        # ---- encoder
+        for l in range(nlev - 1):
+            p, k, sk, s = prefixes[l], self.kernel_sizes[l], self.sample_kernel_sizes[l], self.strides[l]
+            e = cat[l].view(0, ch[l])
+            if l == 0:
+                # unit0 reads the 1-channel fp32 source in place; the 1x1x1 shortcut (Cin=1) is an
+                # affine map of the same source applied in unit1's epilogue.
+                q = p + "0.conv.unit0."
+                w = self._dev(pack_conv_weight(self.sd[q + "conv.weight"], False)[:, 0, :].contiguous())
+                scale, shift, slope, code = fold_epilogue(self.sd, q, ch[0], ch[0], True, "prelu")
+                scale, shift = self._dev(scale), self._dev(shift)
+                ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
+                g = self._geom(k)
+                h = hb[0].view()
+                self._keep += [ep, g, h]
+                fl, nb = _conv_cost(h, h, k, False, 1, ch[0])
+                self.steps.append(_Step("enc0.unit0", self.lib.vsseg_conv3d_cin1,
+                                        (C.byref(self.src), C.byref(h), C.byref(g), w.data_ptr(), C.byref(ep)),
+                                        fl, nb - 4 * _nvox(h) * (ch[0] - 1)))
+                rw = self._dev(self.sd[p + "0.residual.weight"].reshape(-1).float())
+                rbias = self._dev(self.sd[p + "0.residual.bias"].float())
+                self._add_conv("enc0.unit1", p + "0.conv.unit1.", h, e, k, res_cin1=(rw, rbias))
+            else:
+                self._add_ru(f"enc{l}", p + "0.", dn[l - 1].view(), hb[l], rb[l], e, k, 2)
+            self._add_conv(f"down{l}", p + "1.submodule.0.", e, dn[l].view(), sk, stride=s)
+        # ---- bottom
+        pb = prefixes[-1] + "1.submodule.1."
+        kb = self.kernel_sizes[-1]
+        if self.attention:
+            self._add_att("bottom.att", pb + "0.", dn[-1], bot_hid, kb)
+            self._add_ru("bottom", pb + "1.", dn[-1].view(), bot_h, bot_r, bot_o.view(), kb, 2)
+        else:
+            self._add_ru("bottom", pb, dn[-1].view(), bot_h, bot_r, bot_o.view(), kb, 2)
+        # ---- decoder
+        sub_out = bot_o.view()
+        for l in range(nlev - 2, -1, -1):
+            p, k, sk, s = prefixes[l], self.kernel_sizes[l], self.sample_kernel_sizes[l], self.strides[l]
+            self._add_conv(f"up{l}", p + "1.submodule.2.", sub_out, cat[l].view(ch[l], ch[l]), sk, stride=s,
+                           transposed=True)
+            pr = p + "2."
+            if self.attention:
+                self._add_att(f"dec{l}.att", pr + "0.", cat[l], hb[l], k)
+                pr = pr + "1."
+            if l > 0:
+                out = hb[l].view(0, ch[l])
+                self._add_ru(f"dec{l}", pr, cat[l].view(), None, rb[l], out, k, 1)
+                sub_out = out
+            else:
+                # top unit: conv_only + shortcut, both linear -> one conv (shortcut folded into the
+                # centre tap), written to planar fp32 or blended into the sliding-window accumulator.
+                w = pack_conv_weight(self.sd[pr + "conv.unit0.conv.weight"], False).clone()
+                centre = (k[0] // 2 * k[1] + k[1] // 2) * k[2] + k[2] // 2
+                w[centre] += self.sd[pr + "residual.weight"].reshape(self.out_channels, -1).t().float()
+                w = self._dev(w)
+                bias = self._dev((self.sd[pr + "conv.unit0.conv.bias"] + self.sd[pr + "residual.bias"]).float())
+                g = self._geom(k)
+                src = cat[0].view()
+                self._keep += [g, src]
+                fl, nb = _conv_cost(src, src, k, False, src.C, self.out_channels)
+                nb += 4 * _nvox(src) * (self.out_channels * (2 - src.C) + 1)  # out RMW + weight map, not Cin out
+                self.steps.append(_Step("dec0.logits", self.lib.vsseg_conv3d_smallcout,
+                                        (C.byref(src), C.byref(self.dst), C.byref(g), w.data_ptr(), bias.data_ptr(),
+                                         0, 1.0, self.sw_weight), fl, nb))
+        del self.sd
+
+    # -- execution ----------------------------------------------------------------------
+    def _set(self, view, new):
+        C.memmove(C.byref(view), C.byref(new), C.sizeof(_lib.F32View))
+
+    def run(self, src: _lib.F32View, dst: _lib.F32View, sw_weight_ptr: int | None = None, stream=None):
+        """Launch the whole forward for one patch batch.
+
+        src: [B,1,X,Y,Z] fp32 region (may be a strided window of a larger volume);
+        dst: [B,out_channels,X,Y,Z] fp32 region; if ``sw_weight_ptr`` is given the logits are
+        blended (dst += weight * logits) instead of stored.
+        """
+        if (src.B, src.X, src.Y, src.Z) != (self.B, *self.patch) or (dst.B, dst.C, dst.X, dst.Y, dst.Z) != (
+                self.B, self.out_channels, *self.patch):
+            raise ValueError("run(): view shapes do not match the plan")
+        self._set(self.src, src)
+        self._set(self.dst, dst)
+        self.sw_weight.value = sw_weight_ptr
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        for st in self.steps:
+            code = st.fn(*st.args, s)
+            if code:
+                _lib.check(code, st.name)
+        _lib.count_launch(len(self.steps))
+
+    def profile(self, src, dst, sw_weight_ptr=None, iters=3):
+        """Per-step device time (ms, mean of `iters`, CUDA events on the launch stream)."""
+        self._set(self.src, src)
+        self._set(self.dst, dst)
+        self.sw_weight.value = sw_weight_ptr
+        stream = torch.cuda.current_stream(self.device)
+        s = stream.cuda_stream
+        ms = [0.0] * len(self.steps)
+        for it in range(iters + 1):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.steps) + 1)]
+            evs[0].record(stream)
+            for i, st in enumerate(self.steps):
+                _lib.check(st.fn(*st.args, s), st.name)
+                evs[i + 1].record(stream)
+            torch.cuda.synchronize(self.device)
+            if it:  # first pass is a warm-up
+                for i in range(len(self.steps)):
+                    ms[i] += evs[i].elapsed_time(evs[i + 1]) / iters
+        return [(st.name, st.kind, st.flops, st.bytes, t) for st, t in zip(self.steps, ms)]
+
+    def total_flops(self):
+        return sum(st.flops for st in self.steps)
+
+    def forward(self, x: torch.Tensor):
+        """x: [B,1,X,Y,Z] fp32 CUDA tensor -> (logits [B,out,X,Y,Z], att_maps coarsest first)."""
+        if x.device != self.device or x.dtype != torch.float32:
+            raise ValueError("forward(): expects a float32 tensor on the plan's device")
+        out = torch.empty((self.B, self.out_channels, *self.patch), dtype=torch.float32, device=self.device)
+        self.run(f32view(x), f32view(out))
+        return out, list(self.att_maps)
+
+
+def conv_block_ncdhw(x, sd, kernel_size, stride, transposed, norm, act, residual=None):
+    """One fused Convolution block on an NCDHW fp32 CUDA tensor (standalone-module path).
+
+    sd holds conv.weight / conv.bias (/ norm.* / act.weight).  Channels are zero-padded to the
+    act8 granularity (8 in, 16 out) so any channel count works; pack and unpack are native kernels.
+    """
+    lib = _lib.load()
+    if not x.is_cuda:
+        raise _lib.NativeLibraryError("conv_block_ncdhw needs a CUDA tensor (no CPU fallback)")
+    w0 = sd["conv.weight"]
+    cout = w0.shape[1] if transposed else w0.shape[0]
+    B, cin = x.shape[0], x.shape[1]
+    cin8, cout16 = _round_up(cin, 8), _round_up(cout, 16)
+    sd = dict(sd)
+    if sd.get("conv.bias") is None:
+        sd["conv.bias"] = torch.zeros(cout, device=x.device)
+    w = pack_conv_weight(w0, transposed, cout16)
+    if cin8 != cin:
+        w = torch.nn.functional.pad(w, (0, 0, 0, cin8 - cin))
+    w = w.contiguous()
+    scale, shift, slope, code = fold_epilogue(sd, "", cout, cout16, norm, act)
+    xin = x.float()
+    if cin8 != cin:
+        xin = torch.nn.functional.pad(xin, (0, 0, 0, 0, 0, 0, 0, cin8 - cin))
+    src = Act8Buffer(B, cin8, *x.shape[2:], x.device).from_ncdhw(xin)
+    if transposed:
+        odims = [d * s for d, s in zip(x.shape[2:], stride)]
+    else:
+        odims = [(d + s - 1) // s for d, s in zip(x.shape[2:], stride)]
+    dst = Act8Buffer(B, cout16, *odims, x.device)
+    res_v = None
+    if residual is not None:
+        r = torch.nn.functional.pad(residual.float(), (0, 0, 0, 0, 0, 0, 0, cout16 - cout))
+        rbuf = Act8Buffer(B, cout16, *odims, x.device).from_ncdhw(r)
+        res_v = rbuf.view()
+    g = _lib.ConvGeom(*[int(k) for k in kernel_size], *[int(s) for s in stride], 1 if transposed else 0)
+    ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
+    sv, dv = src.view(), dst.view()
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(lib.vsseg_conv3d_act8(C.byref(sv), C.byref(dv), C.byref(g), w.data_ptr(), cout16, C.byref(ep),
+                                     C.byref(res_v) if res_v is not None else None, None, None, None, stream),
+               "conv3d_act8")
+    _lib.count_launch()
+    return dst.to_ncdhw(0, cout16)[:, :cout].contiguous()
+
+
+def native_shortcut(conv: torch.nn.Module, x):
+    """The ResidualUnit shortcut conv (reference convolutions.py:241-250) as a native launch."""
+    sd = {"conv.weight": conv.weight.detach(), "conv.bias": conv.bias.detach() if conv.bias is not None else None}
+    return conv_block_ncdhw(x, sd, conv.kernel_size, conv.stride, False, False, "none")
