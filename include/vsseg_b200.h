@@ -92,6 +92,21 @@ int vsseg_conv3d_act8(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
                       const vsseg_f32view* res_src, const float* res_w, const float* res_b,
                       void* stream);
 
+/*
+ * Tensor-core path of the same fused block for the FLOP-heavy layers: tcgen05.mma (bf16x3 on the
+ * hi/lo planes, fp32 TMEM accumulators), TMA-staged haloed tiles, same epilogue/residual contract
+ * as vsseg_conv3d_act8.  Supported: stride 1, kernel 3x3x{1,3}, Cin and Cout multiples of 16,
+ * Cout <= 96, Z a multiple of 128 (vsseg_conv3d_tc_supported returns 1).
+ *   w_packed: bf16 [Cin/16][dx 3][plane hi,lo][dy 3][dz KZ][khalf 2][Cout][8]
+ *             (element = weight[cout][cin = 16*c + 8*khalf + j][dx][dy][dz], split like act8)
+ */
+int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g);
+int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
+                    const void* w_packed, const vsseg_epilogue* ep,
+                    const vsseg_act8* res_act8,
+                    const vsseg_f32view* res_src, const float* res_w, const float* res_b,
+                    void* stream);
+
 /* First encoder conv: 1-channel fp32 input (read in place from the volume) -> act8.
  * Replaces model.0.conv.unit0 (Conv3d(1,16,(3,3,1)) + BN + PReLU).  w: fp32 [taps][Cout]. */
 int vsseg_conv3d_cin1(const vsseg_f32view* in, const vsseg_act8* out, const vsseg_conv_geom* g,

@@ -182,3 +182,44 @@ def test_finalize_mask_and_dice():
     s = sums.cpu()[0]
     dice = (2 * s[0] + 1e-5) / (s[1] + s[2] + 1e-5)
     assert abs(dice.item() - loss_oracle.dice_score(ref, label).item()) < 1e-6
+
+
+TC_CASES = [
+    # B, cin, cout, X, Y, k
+    (1, 32, 48, 8, 8, (3, 3, 3)),    # tile 2x4, level-3 encoder shape
+    (1, 96, 48, 4, 6, (3, 3, 3)),    # tile 2x2, level-3 decoder conv
+    (2, 16, 16, 5, 3, (3, 3, 1)),    # tile 1x1, odd sizes, batch 2, k=(3,3,1)
+    (1, 64, 32, 6, 4, (3, 3, 1)),    # tile 2x4
+    (1, 16, 32, 3, 2, (3, 3, 1)),    # tile 1x2
+    (1, 48, 96, 2, 4, (3, 3, 3)),    # widest N that fits TMEM with 2x2 lines
+]
+
+
+@pytest.mark.parametrize("B,cin,cout,X,Y,k", TC_CASES)
+def test_tcgen05_conv_matches_oracle(B, cin, cout, X, Y, k):
+    """The tcgen05/TMA implicit-GEMM conv (Z = 128 lines) vs torch fp32 on the CPU, with BN, PReLU and
+    a residual; also checks that the tensor-core path (not the generic kernel) is the one that ran."""
+    import ctypes as C
+    from params.networks.blocks.convolutions import Convolution
+    from vs_seg_b200 import lib as vlib
+    from vs_seg_b200.tensors import Act8Buffer
+    dev = _dev()
+    torch.manual_seed(B * 7 + cin + cout)
+    blk = Convolution(3, cin, cout, strides=1, kernel_size=k, act="PRELU", norm="BATCH", dropout=0.1)
+    with torch.no_grad():
+        blk.norm.running_mean.normal_(0, 0.2)
+        blk.norm.running_var.uniform_(0.5, 1.5)
+        blk.norm.weight.uniform_(0.7, 1.3)
+        blk.norm.bias.normal_(0, 0.2)
+    blk.eval()
+    x = torch.randn(B, cin, X, Y, 128)
+    res = torch.randn(B, cout, X, Y, 128)
+    a, b = Act8Buffer(B, cin, X, Y, 128, dev), Act8Buffer(B, cout, X, Y, 128, dev)
+    g = vlib.ConvGeom(*k, 1, 1, 1, 0)
+    va, vb = a.view(), b.view()
+    assert vlib.load().vsseg_conv3d_tc_supported(C.byref(va), C.byref(vb), C.byref(g)) == 1
+    with torch.no_grad():
+        ref = blk(x) + res
+        got = blk.to(dev)._native_forward(x.to(dev), residual=res.to(dev)).cpu()
+    err = (got - ref).abs().max().item()
+    assert err < 5e-5 * max(1.0, ref.abs().max().item()), err

@@ -1,0 +1,45 @@
+"""Per-launch device time of one 128^3 patch forward (CUDA events), written as a TSV.
+Usage (GPU box): python tools/profile_plan.py [out.tsv]"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from vs_seg_b200 import sliding_window as sw  # noqa: E402
+from vs_seg_b200.tensors import f32view  # noqa: E402
+
+
+def main():
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "plan_profile.tsv")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    dev = torch.device("cuda:0")
+    net, _ = bench.build_net(dev)
+    roi = bench.ROI
+    plan = net.eval_plan(roi, 1, dev)
+    vol = torch.randn((1, 1) + bench.VOLUME, device=dev)
+    acc = torch.zeros((1, 2) + bench.VOLUME, device=dev)
+    imap = sw.importance_map(roi, "gaussian", 0.125, dev)
+    prof = plan.profile(f32view(vol, (0, 0, 0), roi), f32view(acc, (0, 0, 0), roi), imap.data_ptr(), iters=5)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    tot = sum(p[4] for p in prof)
+    lines = ["name\tkind\tGFLOP\tMB\tms\tshare\tTFLOP/s\tGB/s\troof_ms\tfrac_of_roof"]
+    roof_tot = 0.0
+    for name, kind, fl, nb, ms in prof:
+        roof = max(fl / (peaks["bf16_tflops"] * 1e12), nb / (peaks["hbm_gbs"] * 1e9)) * 1e3
+        roof_tot += roof
+        lines.append(f"{name}\t{kind}\t{fl / 1e9:.3f}\t{nb / 1e6:.2f}\t{ms:.4f}\t{ms / tot:.3f}\t"
+                     f"{fl / ms / 1e9:.2f}\t{nb / ms / 1e6:.1f}\t{roof:.4f}\t{roof / ms:.3f}")
+    lines.append(f"TOTAL\t-\t{sum(p[2] for p in prof) / 1e9:.2f}\t{sum(p[3] for p in prof) / 1e6:.1f}\t{tot:.3f}\t1\t"
+                 f"{sum(p[2] for p in prof) / tot / 1e9:.2f}\t{sum(p[3] for p in prof) / tot / 1e6:.1f}\t"
+                 f"{roof_tot:.4f}\t{roof_tot / tot:.3f}")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,24 @@ def pack_conv_weight(w: torch.Tensor, transposed: bool, cout_pad: int | None = N
     return p.contiguous()
 
 
+def pack_conv_weight_tc(w: torch.Tensor) -> torch.Tensor:
+    """Conv3d weight [Cout,Cin,3,3,KZ] -> bf16 [Cin/16][dx][plane hi/lo][dy][dz][khalf][Cout][8]
+    (the shared-memory image vsseg_conv3d_tc streams with cp.async.bulk; include/vsseg_b200.h)."""
+    cout, cin, kx, ky, kz = w.shape
+    w = w.float()
+    hi = w.bfloat16()
+    lo = (w - hi.float()).bfloat16()
+    p = torch.stack([hi, lo])  # [plane, Cout, Cin, dx, dy, dz]
+    p = p.reshape(2, cout, cin // 16, 2, 8, kx, ky, kz)  # Cin -> (c16, khalf, j)
+    p = p.permute(2, 5, 0, 6, 7, 3, 1, 4)  # [c16, dx, plane, dy, dz, khalf, Cout, j]
+    return p.contiguous()
+
+
+def tc_enabled() -> bool:
+    import os
+    return os.environ.get("VSSEG_TC", "1") != "0"
+
+
 def fold_epilogue(sd, p, cout, cout_pad, norm: bool, act: str):
     """Per-channel scale/shift of conv bias + eval BatchNorm3d (eps 1e-5), and the activation."""
     bias = sd[p + "conv.bias"].double()
@@ -99,8 +117,9 @@ class UNetEvalPlan:
                  strides=((2, 2, 1), (2, 2, 1), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
                  kernel_sizes=((3, 3, 1), (3, 3, 1), (3, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
                  sample_kernel_sizes=((3, 3, 1), (3, 3, 1), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
-                 in_channels=1, out_channels=2):
+                 in_channels=1, out_channels=2, tensor_cores=None):
         self.lib = _lib.load()
+        self.use_tc = tc_enabled() if tensor_cores is None else bool(tensor_cores)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.NativeLibraryError("UNetEvalPlan runs on a CUDA device only (no CPU fallback)")
@@ -148,21 +167,23 @@ class UNetEvalPlan:
         """src/dst: Act8 views.  One fused Convolution block (+ optional residual)."""
         cout = dst.C
         cpad = _round_up(cout, 16)
-        w = self._dev(pack_conv_weight(self.sd[p + "conv.weight"], transposed, cpad))
         scale, shift, slope, code = fold_epilogue(self.sd, p, cout, cpad, norm, act)
         scale, shift = self._dev(scale), self._dev(shift)
         ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
         g = self._geom(k, stride, transposed)
         res_p = C.byref(res) if res is not None else None
-        if res_cin1 is not None:
-            rw, rb = res_cin1
-            args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep), None,
-                    C.byref(self.src), rw.data_ptr(), rb.data_ptr())
-        else:
-            args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep), res_p, None, None, None)
+        tail = (None, C.byref(self.src), res_cin1[0].data_ptr(), res_cin1[1].data_ptr()) if res_cin1 is not None \
+            else (res_p, None, None, None)
         self._keep += [src, dst, g, ep, res]
         extra = _nvox(dst) * cout if res is not None else (_nvox(dst) if res_cin1 is not None else 0)
         fl, nb = _conv_cost(src, dst, k, transposed, src.C, cout, extra)
+        if self.use_tc and self.lib.vsseg_conv3d_tc_supported(C.byref(src), C.byref(dst), C.byref(g)):
+            w = self._dev(pack_conv_weight_tc(self.sd[p + "conv.weight"]))
+            args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), C.byref(ep)) + tail
+            self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc, args, fl, nb, kind="tcgen05"))
+            return
+        w = self._dev(pack_conv_weight(self.sd[p + "conv.weight"], transposed, cpad))
+        args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep)) + tail
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
 
     def _add_shortcut(self, name, p, src, dst):
@@ -391,9 +412,15 @@ def conv_block_ncdhw(x, sd, kernel_size, stride, transposed, norm, act, residual
     ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
     sv, dv = src.view(), dst.view()
     stream = torch.cuda.current_stream(x.device).cuda_stream
-    _lib.check(lib.vsseg_conv3d_act8(C.byref(sv), C.byref(dv), C.byref(g), w.data_ptr(), cout16, C.byref(ep),
-                                     C.byref(res_v) if res_v is not None else None, None, None, None, stream),
-               "conv3d_act8")
+    res_p = C.byref(res_v) if res_v is not None else None
+    if tc_enabled() and cin8 == cin and cout16 == cout and lib.vsseg_conv3d_tc_supported(
+            C.byref(sv), C.byref(dv), C.byref(g)):
+        wt = pack_conv_weight_tc(w0)
+        _lib.check(lib.vsseg_conv3d_tc(C.byref(sv), C.byref(dv), C.byref(g), wt.data_ptr(), C.byref(ep), res_p,
+                                       None, None, None, stream), "conv3d_tc")
+    else:
+        _lib.check(lib.vsseg_conv3d_act8(C.byref(sv), C.byref(dv), C.byref(g), w.data_ptr(), cout16, C.byref(ep),
+                                         res_p, None, None, None, stream), "conv3d_act8")
     _lib.count_launch()
     return dst.to_ncdhw(0, cout16)[:, :cout].contiguous()
 
