@@ -93,18 +93,40 @@ int vsseg_conv3d_act8(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
                       void* stream);
 
 /*
- * Tensor-core path of the same fused block for the FLOP-heavy layers: tcgen05.mma (bf16x3 on the
- * hi/lo planes, fp32 TMEM accumulators), TMA-staged haloed tiles, same epilogue/residual contract
- * as vsseg_conv3d_act8.  Supported: stride 1, kernel 3x3x{1,3}, Cin and Cout multiples of 16,
- * Cout <= 96, Z a multiple of 128 (vsseg_conv3d_tc_supported returns 1).
- *   w_packed: bf16 [Cin/16][dx 3][plane hi,lo][dy 3][dz KZ][khalf 2][Cout][8]
- *             (element = weight[cout][cin = 16*c + 8*khalf + j][dx][dy][dz], split like act8)
+ * Tensor-core path of the same fused block: tcgen05.mma (bf16x3 on the hi/lo planes, fp32 TMEM
+ * accumulators), TMA-staged input boxes, same epilogue/residual contract as vsseg_conv3d_act8.
+ * Covers Conv3d (stride 1 or 2 per axis, kernel 1 or 3 per axis) and ConvTranspose3d (stride (2,2,1|2),
+ * kernel (3,3,1|3), output_padding = stride-1; reference convolutions.py:114-135) with Cin % 16 == 0,
+ * Cout % 8 == 0 and a z extent of the M grid (output grid; input grid when transposed) that is a
+ * multiple of 128 or one of 8..64 dividing 128.  vsseg_conv3d_tc_supported returns 1 when the shape is
+ * covered; vsseg_conv3d_tc_suggest_split returns the n_split (CTAs per M tile along Cout) that fills
+ * the chip for small layers, or 0 when the shape is not covered.
+ *
+ *   w_packed: bf16 [sel][Cin/16][j][plane hi,lo][tz][khalf 2][ty'][n_cta][8], n_cta = round_up(Cout,16)/n_split
+ *     Conv3d:          sel = n-slice, j = kernel x index, ty' = ky-1-ty (reversed kernel y index, so that the
+ *                      taps sharing one staged input line are adjacent N rows of a single MMA), tz = kernel z,
+ *                      element = W[cout = sel*n_cta + n][cin = 16*c + 8*khalf + e][j][ty][tz]
+ *     ConvTranspose3d: sel = px*n_split + n-slice (px = output x parity), j in {0,1} = input x shift, ty' = ty,
+ *                      element = W[cin][cout][kx][ty][tz] with kx = 1 (px=0, j=0; j=1 unused, zeros),
+ *                      kx = 2 (px=1, j=0), kx = 0 (px=1, j=1)
+ *     each value split hi/lo like act8; channels >= Cout are zero.
+ *   shortcut_src (optional): input of a fused 1x1x1 ResidualUnit shortcut conv
+ *     (convolutions.py:241-255) accumulated in a second TMEM accumulator and added after the
+ *     activation: out = act(BN(conv(in))) + shortcut_w * shortcut_src + shortcut_bias.
+ *     shortcut_w: bf16 [n-slice][Csrc/16][plane][khalf][n_cta][8]; stride-1 convs only.
  */
-int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g);
+int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
+                              int32_t n_split, const vsseg_act8* shortcut_src);
+int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
+                                  const vsseg_act8* shortcut_src);
+/* Human-readable description of the launch plan (tile, stages, op table) for tests and DESIGN.md. */
+int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
+                             int32_t n_split, const vsseg_act8* shortcut_src, char* buf, int32_t buflen);
 int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
-                    const void* w_packed, const vsseg_epilogue* ep,
+                    const void* w_packed, int32_t n_split, const vsseg_epilogue* ep,
                     const vsseg_act8* res_act8,
                     const vsseg_f32view* res_src, const float* res_w, const float* res_b,
+                    const vsseg_act8* shortcut_src, const void* shortcut_w, const float* shortcut_bias,
                     void* stream);
 
 /* First encoder conv: 1-channel fp32 input (read in place from the volume) -> act8.

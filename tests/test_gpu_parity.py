@@ -185,41 +185,86 @@ def test_finalize_mask_and_dice():
 
 
 TC_CASES = [
-    # B, cin, cout, X, Y, k
-    (1, 32, 48, 8, 8, (3, 3, 3)),    # tile 2x4, level-3 encoder shape
-    (1, 96, 48, 4, 6, (3, 3, 3)),    # tile 2x2, level-3 decoder conv
-    (2, 16, 16, 5, 3, (3, 3, 1)),    # tile 1x1, odd sizes, batch 2, k=(3,3,1)
-    (1, 64, 32, 6, 4, (3, 3, 1)),    # tile 2x4
-    (1, 16, 32, 3, 2, (3, 3, 1)),    # tile 1x2
-    (1, 48, 96, 2, 4, (3, 3, 3)),    # widest N that fits TMEM with 2x2 lines
+    # B, cin, cout, (X, Y, Z), k, stride, transposed
+    (1, 32, 48, (8, 8, 128), (3, 3, 3), (1, 1, 1), False),    # level-3 encoder shape, z halo in the box
+    (1, 96, 48, (4, 6, 128), (3, 3, 3), (1, 1, 1), False),    # level-3 decoder conv
+    (2, 16, 16, (5, 3, 128), (3, 3, 1), (1, 1, 1), False),    # odd sizes, batch 2, k=(3,3,1)
+    (1, 64, 32, (6, 4, 256), (3, 3, 1), (1, 1, 1), False),    # two z tiles
+    (1, 48, 96, (2, 4, 128), (3, 3, 3), (1, 1, 1), False),    # wide N
+    (1, 48, 64, (6, 8, 64), (3, 3, 3), (1, 1, 1), False),     # Z=64: 2 lines per M tile, per-dz boxes
+    (2, 64, 80, (4, 8, 32), (3, 3, 3), (1, 1, 1), False),     # Z=32: 4 lines per M tile
+    (1, 80, 96, (4, 8, 16), (3, 3, 3), (1, 1, 1), False),     # Z=16: 8 lines per M tile (bottom level)
+    (1, 80, 40, (4, 8, 16), (3, 3, 3), (1, 1, 1), False),     # Cout=40 (attention hidden): N padded to 48
+    (1, 16, 32, (4, 4, 128), (1, 1, 1), (1, 1, 1), False),    # 1x1x1 conv
+    (1, 16, 16, (8, 12, 128), (3, 3, 1), (2, 2, 1), False),   # downsample (2,2,1)
+    (1, 48, 48, (8, 8, 128), (3, 3, 3), (2, 2, 2), False),    # downsample (2,2,2): traversal strides
+    (2, 64, 64, (4, 8, 64), (3, 3, 3), (2, 2, 2), False),     # downsample, small z
+    (1, 32, 16, (4, 6, 128), (3, 3, 1), (2, 2, 1), True),     # upsample (2,2,1): 4 phases
+    (1, 64, 48, (4, 4, 64), (3, 3, 3), (2, 2, 2), True),      # upsample (2,2,2): 8 phases
+    (2, 96, 80, (2, 8, 16), (3, 3, 3), (2, 2, 2), True),      # bottom upsample, N=80
+    (1, 80, 96, (4, 4, 16), (3, 3, 3), (1, 1, 1), False),     # bottom level of a 128^3 patch: half-empty M tile
+    (1, 80, 80, (8, 8, 32), (3, 3, 3), (2, 2, 2), False),     # downsample into the bottom level
+    (1, 96, 80, (4, 4, 16), (3, 3, 3), (2, 2, 2), True),      # upsample out of the bottom level
 ]
 
 
-@pytest.mark.parametrize("B,cin,cout,X,Y,k", TC_CASES)
-def test_tcgen05_conv_matches_oracle(B, cin, cout, X, Y, k):
-    """The tcgen05/TMA implicit-GEMM conv (Z = 128 lines) vs torch fp32 on the CPU, with BN, PReLU and
-    a residual; also checks that the tensor-core path (not the generic kernel) is the one that ran."""
-    import ctypes as C
+def _seeded_block(cin, cout, k, stride, transposed, seed):
     from params.networks.blocks.convolutions import Convolution
-    from vs_seg_b200 import lib as vlib
-    from vs_seg_b200.tensors import Act8Buffer
-    dev = _dev()
-    torch.manual_seed(B * 7 + cin + cout)
-    blk = Convolution(3, cin, cout, strides=1, kernel_size=k, act="PRELU", norm="BATCH", dropout=0.1)
+    torch.manual_seed(seed)
+    blk = Convolution(3, cin, cout, strides=stride, kernel_size=k, act="PRELU", norm="BATCH", dropout=0.1,
+                      is_transposed=transposed)
     with torch.no_grad():
         blk.norm.running_mean.normal_(0, 0.2)
         blk.norm.running_var.uniform_(0.5, 1.5)
         blk.norm.weight.uniform_(0.7, 1.3)
         blk.norm.bias.normal_(0, 0.2)
-    blk.eval()
-    x = torch.randn(B, cin, X, Y, 128)
-    res = torch.randn(B, cout, X, Y, 128)
-    a, b = Act8Buffer(B, cin, X, Y, 128, dev), Act8Buffer(B, cout, X, Y, 128, dev)
-    g = vlib.ConvGeom(*k, 1, 1, 1, 0)
-    va, vb = a.view(), b.view()
-    assert vlib.load().vsseg_conv3d_tc_supported(C.byref(va), C.byref(vb), C.byref(g)) == 1
+    return blk.eval()
+
+
+@pytest.mark.parametrize("B,cin,cout,dims,k,stride,transposed", TC_CASES)
+def test_tcgen05_conv_matches_oracle(B, cin, cout, dims, k, stride, transposed):
+    """The tcgen05/TMA implicit-GEMM conv vs torch fp32 on the CPU, with BN, PReLU and a residual;
+    require_tc proves the tensor-core path (not the generic kernel) is the one that ran."""
+    from vs_seg_b200.engine import conv_block_ncdhw
+    dev = _dev()
+    blk = _seeded_block(cin, cout, k, stride, transposed, B * 7 + cin + cout)
+    x = torch.randn(B, cin, *dims)
     with torch.no_grad():
-        ref = blk(x) + res
-        got = blk.to(dev)._native_forward(x.to(dev), residual=res.to(dev)).cpu()
+        ref = blk(x)
+        res = torch.randn_like(ref)
+        ref = ref + res
+        sd = {"conv." + n: v for n, v in blk.conv.state_dict().items()}
+        sd.update({"norm." + n: v for n, v in blk.norm.state_dict().items()})
+        sd["act.weight"] = blk.act.weight
+        sd = {n: v.to(dev) for n, v in sd.items()}
+        got = conv_block_ncdhw(x.to(dev), sd, k, stride, transposed, True, "prelu", residual=res.to(dev),
+                               require_tc=True).cpu()
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    assert err < 5e-5 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("B,cin,csrc,cout,dims,k", [
+    (1, 32, 16, 32, (6, 8, 128), (3, 3, 1)),   # encoder unit1 + shortcut of the unit input
+    (1, 48, 32, 48, (4, 8, 128), (3, 3, 3)),   # level 3, z halo
+    (2, 64, 48, 64, (4, 4, 64), (3, 3, 3)),    # small z
+    (1, 96, 96, 48, (4, 4, 128), (3, 3, 3)),   # decoder unit0: shortcut of the same input
+])
+def test_tcgen05_fused_shortcut(B, cin, csrc, cout, dims, k):
+    """ResidualUnit sum with the 1x1x1 shortcut as a second TMEM accumulator (convolutions.py:241-255)."""
+    from vs_seg_b200.engine import conv_block_ncdhw
+    dev = _dev()
+    blk = _seeded_block(cin, cout, k, (1, 1, 1), False, cin + csrc)
+    sc = torch.nn.Conv3d(csrc, cout, 1)
+    x, xs = torch.randn(B, cin, *dims), torch.randn(B, csrc, *dims)
+    with torch.no_grad():
+        ref = blk(x) + sc(xs)
+        sd = {"conv." + n: v for n, v in blk.conv.state_dict().items()}
+        sd.update({"norm." + n: v for n, v in blk.norm.state_dict().items()})
+        sd["act.weight"] = blk.act.weight
+        sd = {n: v.to(dev) for n, v in sd.items()}
+        got = conv_block_ncdhw(x.to(dev), sd, k, (1, 1, 1), False, True, "prelu",
+                               shortcut=(xs.to(dev), sc.weight.detach().to(dev), sc.bias.detach().to(dev)),
+                               require_tc=True).cpu()
     err = (got - ref).abs().max().item()
     assert err < 5e-5 * max(1.0, ref.abs().max().item()), err

@@ -1,22 +1,23 @@
-// Tensor-core (tcgen05 + TMEM + TMA) implicit-GEMM 3-D convolution for the FLOP-heavy stride-1
-// layers of UNet2d5_spvPA (reference params/networks/blocks/convolutions.py:137-156), sm_100a only.
+// Tensor-core (tcgen05 + TMEM + TMA) implicit-GEMM 3-D convolution of UNet2d5_spvPA, sm_100a only.
+// Covers every Conv3d / ConvTranspose3d of the network whose channels are multiples of 16/8
+// (reference params/networks/blocks/convolutions.py:125-156): stride-1 "same" convs, the strided
+// downsample convs, the transposed (sub-pixel phase decomposed) upsample convs and the 1x1x1
+// ResidualUnit shortcut fused as a second accumulator (convolutions.py:241-255).
 //
-// GEMM view: M = 128 consecutive z voxels of one (x,y) line, N = Cout, K = Cin x taps.
-// Operands are the two bf16 planes of the act8 layout (value = hi + lo), and every product is
-// evaluated as hi*hi + lo*hi + hi*lo ("bf16x3") into one fp32 TMEM accumulator, which keeps the
-// network inside the 1e-3 parity bar that single-pass bf16/tf32 misses.
+// GEMM view.  An M tile is 128 positions of the "M grid" (the output grid of a conv, the INPUT grid
+// of a transposed conv): LY consecutive y lines x LZ consecutive z (LY*LZ = 128, LZ = min(Z,128)).
+// N = a slice of Cout, K = Cin x taps walked as stages (16-channel chunk c, x tap j).  Operands
+// are the two bf16 planes of the act8 layout (value = hi + lo); every product is evaluated as
+// hi*hi + lo*hi + hi*lo ("bf16x3") into one fp32 TMEM accumulator, which keeps the network inside
+// the 1e-3 parity bar that single-pass bf16/tf32 misses.
 //
-// Data flow per CTA (a tile of XT x YT output lines, all Cout channels):
-//   for each 16-channel slice of Cin:
-//     for each halo x-plane px in [x0-1, x0+XT]:
-//       TMA (5-D tiled, OOB zero fill = "same" padding) stages the haloed slab
-//         [cg 2][y0-1 .. y0+YT][z0-hz .. z0+127+hz][8 ch]   for the hi and the lo plane  -> smem ring
-//       cp.async.bulk stages the packed weights of every tap with this dx (3 slots, one per dx)
-//       one thread issues tcgen05.mma for every (output line, dy, dz) that reads this plane:
-//         the A descriptor is just a start-address offset into the slab (no-swizzle K-major
-//         layout, rows 16 B apart), so each staged element is reused by up to 9*XT... taps from
-//         shared memory instead of being re-fetched from L2 per tap.
-//   epilogue warps: tcgen05.ld -> BN scale/shift -> PReLU/ReLU -> (+ residual) -> split-bf16 -> global.
+// A CTA owns NACC accumulators (y line groups x output phases) of one x row.  Per stage the TMA
+// producer stages a few boxes of the input (5-D tiled map; OOB zero fill = "same" padding and the
+// output_padding row of the transposed conv; traversal strides = conv stride) plus the packed
+// weights of the stage; the single MMA thread then walks a host-built op table
+// (A offset, B offset, accumulator) - the shifted views of the staged boxes ARE the im2col matrix,
+// nothing is gathered by threads.  Epilogue warps: tcgen05.ld -> BN scale/shift -> PReLU/ReLU ->
+// (+ residual / + shortcut accumulator) -> split-bf16 -> global (act8).
 #include <cuda.h>
 
 #include "vsseg_common.cuh"
@@ -46,20 +47,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -95,6 +97,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 format: version 1 at bit 46).
@@ -109,188 +126,296 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// ---- host-built tables ------------------------------------------------------------------------
+struct TcOp {        // one tcgen05.mma: D[128 x n8*8 columns at col] += A[128 x 16] * B[16 x n8*8]
+    uint16_t a16;    // A start offset inside the stage (hi or lo plane included), in 16 B units
+    uint16_t b16;    // B start offset inside the stage's B region (hi or lo plane included), 16 B units
+    uint16_t col;    // first TMEM column written
+    uint16_t n8;     // N / 8 of this instruction (several adjacent accumulators share one A read)
+};
+struct TcBox {       // one TMA box of a stage (issued for the hi and the lo plane)
+    uint16_t dst16;  // offset inside the hi-plane A region, 16 B units
+    int8_t dy, dz;   // input-coordinate shift of the box origin
+};
+struct TcAcc {       // where an accumulator lands in the output
+    int16_t y_add;   // output y of M-tile line 0, relative to the tile's output y base
+    int8_t z_add;    // output z phase
+    int8_t pad;
+};
+
+constexpr int TC_MAX_OPS = 144;
+constexpr int TC_MAX_OPS2 = 48;
+constexpr int TC_MAX_BOX = 9;
+constexpr int TC_MAX_ACC = 32;
+
 struct TcArgs {
     vsseg_act8 out;
     vsseg_epilogue ep;
-    int res_mode;
+    int res_mode;            // 0 none, 1 act8 addend, 2 cin1 affine
     vsseg_act8 res;
     vsseg_f32view rsrc;
     const float* res_w;
     const float* res_b;
-    const __nv_bfloat16* w;  // packed [Cin/16][3 dx][2 plane][3 dy][KZ][2 khalf][Cout][8]
-    int Cin, Cout, X, Y, Z, B, KZ;
-    int XT, YT, SA;          // tile lines and A-ring depth
-    int cg_plane, cg_batch;  // merged-cg index strides of the TMA map (lo plane, batch)
-    uint32_t a_block, a_box_bytes, a_stage, b_slot, tmem_cols;
+    const float* bias2;      // shortcut bias [Cout] (segment 2)
+    const uint8_t* w;        // packed main weights  [sel][chunk][j][b_bytes]
+    const uint8_t* w2;       // packed shortcut weights [nsel][chunk2][b2_bytes]
+    int nchunk, nj, nchunk2; // stages: nchunk*nj main + nchunk2 shortcut
+    int nop, nop2, nbox, nacc;
+    int nstage;              // ring depth
+    uint32_t a_plane, b_plane, b_off, stage_bytes;  // hi->lo distance of A / B inside a stage, B region start
+    uint32_t box_tx, b_bytes, b2_bytes, b2_plane;   // bytes of one box (one plane), of the weight slices
+    uint32_t lbo_a, lbo_b, lbo_b2, idesc, tmem_cols;
+    // tile decomposition of the M grid
+    int ntz, nty, ntx, nsel, npx, nsplit;
+    int LZ, LY, YL, Ym;      // M-tile shape, y lines of the M grid per CTA tile, y extent of the M grid
+    int n_cta;               // output channels per CTA (multiple of 16), n_real: channels to store
+    int cout;                // real Cout (multiple of 8)
+    // input coordinates of box origin: x = mx*sx + j + xoff ; y = my0*sy + box.dy ; z = mz0*sz + box.dz
+    int sx, sy, sz, xoff, Xin;
+    int cg_plane, cg_batch;        // merged-cg index strides of the main map (lo plane, batch)
+    int cg_plane2, cg_batch2;      // same for the shortcut source
+    // output coordinates: ox = mx*ux + px ; oy = (my0 + ly)*uy + acc.y_add ; oz = (mz0 + zz)*uz + acc.z_add
+    int ux, uy, uz;
+    int dy2, dz2;            // box origin shift of the shortcut source
+    // line mode (M tile = one z line of 128): A staged by per-line bulk copies instead of tensor-map boxes
+    int line_mode, BY, pitch, hy, hz, Yin, Zin;
+    vsseg_act8 in, in2;
+    TcOp ops[TC_MAX_OPS];
+    TcOp ops2[TC_MAX_OPS2];
+    TcBox boxes[TC_MAX_BOX];
+    TcAcc accs[TC_MAX_ACC];
 };
 
 constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                             const __grid_constant__ CUtensorMap tmap2,
+                                                             const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);  // [SA]
-    uint64_t* a_empty = a_full + 8;                        // [SA]
-    uint64_t* b_full = a_full + 16;                        // [3]
-    uint64_t* b_empty = a_full + 20;                       // [3]
-    uint64_t* acc_full = a_full + 24;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_full + 26);
-    uint8_t* a_ring = smem + 1024;
-    uint8_t* b_ring = a_ring + (size_t)a.SA * a.a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [nstage]
+    uint64_t* empty = full + 8;                          // [nstage]
+    uint64_t* acc_full = full + 16;
+    uint64_t* tmem_zero = full + 17;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 18);
+    const uint32_t ring = smem_u32(smem) + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int XT = a.XT, YT = a.YT, KZ = a.KZ, hz = KZ == 3 ? 1 : 0, ZH = 128 + 2 * hz;
     // tile coordinates
     int t = blockIdx.x;
-    const int ntz = a.Z / 128, nty = a.Y / YT, ntx = a.X / XT;
-    const int tz = t % ntz; t /= ntz;
-    const int ty = t % nty; t /= nty;
-    const int tx = t % ntx; t /= ntx;
+    const int sel = t % a.nsel; t /= a.nsel;
+    const int tz = t % a.ntz; t /= a.ntz;
+    const int ty = t % a.nty; t /= a.nty;
+    const int mx = t % a.ntx; t /= a.ntx;
     const int b = t;
-    const int x0 = tx * XT, y0 = ty * YT, z0 = tz * 128;
-    const int nchunk = a.Cin / 16;
-    const uint32_t slab = (uint32_t)ZH * 16;             // one (cg, line) slab
-    const uint32_t lbo_a = (uint32_t)(YT + 2) * slab;     // cg -> cg+1
-    const uint32_t b_tap = (uint32_t)a.Cout * 32;         // one tap of one plane: [2 khalf][Cout][8] bf16
-    const uint32_t b_plane = (uint32_t)(3 * KZ) * b_tap;  // one plane of a slot
+    const int px = sel / a.nsplit, ns = sel % a.nsplit;
+    const int my0 = ty * a.YL, mz0 = tz * a.LZ;
+    const int nmain = a.nchunk * a.nj, ntot = nmain + a.nchunk2;
+    const int njx = (a.npx == 2 && px == 0) ? 1 : a.nj;  // transposed conv, even x phase: only the centre x tap
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < a.SA; ++i) {
-            mbar_init(a_full + i, 1);
-            mbar_init(a_empty + i, 1);
-        }
-        for (int i = 0; i < 3; ++i) {
-            mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 1);
+        for (int i = 0; i < a.nstage; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, 1);
         }
         mbar_init(acc_full, 1);
+        mbar_init(tmem_zero, 4);
         fence_barrier_init();
     }
+    if (warp == 0 && lane == 0 && !a.line_mode) {
+        prefetch_tmap(&tmap);
+        if (a.nchunk2) prefetch_tmap(&tmap2);
+    }
     if (warp == 1) tmem_alloc(tmem_ptr, a.tmem_cols);
+    if (a.line_mode) {
+        // padding lines / halo rows of the staged tile are never written by the bulk copies: zero the ring once
+        const int ylo = my0 * a.sy - a.hy;
+        if (a.hz > 0 || ylo < 0 || ylo + a.BY > a.Yin) {
+            uint4* q = reinterpret_cast<uint4*>(smem + 1024);
+            const int n16 = (int)(a.nstage * a.stage_bytes / 16);
+            for (int i = threadIdx.x; i < n16; i += TC_THREADS) q[i] = make_uint4(0, 0, 0, 0);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
-        if (lane == 0) {
+    if (warp == 0 && a.line_mode) {
+        // ===== bulk-copy producer: every lane issues whole z lines (2 KB contiguous in act8) =====
+        int it = 0;
+        for (int s = 0; s < ntot; ++s) {
+            const bool seg2 = s >= nmain;
+            const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
+            const int x = seg2 ? mx : mx * a.sx + j + a.xoff;
+            if (x < 0 || x >= a.Xin || j >= njx) continue;
+            const int st = it % a.nstage;
+            mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+            const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+            const vsseg_act8& src = seg2 ? a.in2 : a.in;
+            // staged lines i in [i0, i1): input y = ybase + i; rows z in [zlo, zhi)
+            const int sy = seg2 ? 1 : a.sy;
+            const int ybase = my0 * sy - a.hy;
+            int i0 = seg2 ? a.hy : 0, i1 = seg2 ? a.hy + a.YL : a.BY;
+            i0 = max(i0, -ybase);
+            i1 = min(i1, a.Yin - ybase);
+            const int zlo = max(mz0 - a.hz, 0), zhi = min(mz0 + a.LZ + a.hz, a.Zin);
+            const uint32_t row_bytes = (uint32_t)(zhi - zlo) * 16;
+            const int ncopy = max(i1 - i0, 0) * 4;
+            if (lane == 0) {
+                const uint32_t bb = seg2 ? a.b2_bytes : a.b_bytes;
+                mbar_expect_tx(full + st, (uint32_t)ncopy * row_bytes + bb);
+                const uint8_t* wsrc = seg2 ? a.w2 + ((size_t)ns * a.nchunk2 + c) * a.b2_bytes
+                                           : a.w + ((size_t)(sel * a.nchunk + c) * a.nj + j) * a.b_bytes;
+                bulk_load(base + a.b_off, wsrc, bb, full + st);
+            }
+            const __nv_bfloat16* g0 = (const __nv_bfloat16*)src.hi + (int64_t)b * src.batch_stride;
+            for (int q = lane; q < ncopy; q += 32) {
+                const int i = i0 + (q >> 2), plane = (q >> 1) & 1, cg = q & 1;
+                const __nv_bfloat16* gp = g0 + (int64_t)plane * src.lo_offset +
+                                          ((((int64_t)(2 * c + cg) * a.Xin + x) * a.Yin + (ybase + i)) * a.Zin + zlo) * 8;
+                const uint32_t dst = base + (uint32_t)plane * a.a_plane + (uint32_t)cg * a.lbo_a +
+                                     (uint32_t)(i * a.pitch + (zlo - (mz0 - a.hz))) * 16;
+                bulk_load(dst, gp, row_bytes, full + st);
+            }
+            __syncwarp();
+            ++it;
+        }
+    } else if (warp == 0) {
+        if (elect_one()) {
             // ===== TMA producer =====
             int it = 0;
-            for (int c = 0; c < nchunk; ++c) {
-                for (int s = 0; s < XT + 2; ++s) {
-                    if (s < 3) {  // weights of taps with dx = s for this channel slice
-                        mbar_wait(b_empty + s, (c & 1) ^ 1);
-                        mbar_expect_tx(b_full + s, a.b_slot);
-                        bulk_load(b_ring + (size_t)s * a.b_slot, (const uint8_t*)a.w + ((size_t)c * 3 + s) * a.b_slot,
-                                  a.b_slot, b_full + s);
+            for (int s = 0; s < ntot; ++s) {
+                const bool seg2 = s >= nmain;
+                const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
+                const int x = seg2 ? mx : mx * a.sx + j + a.xoff;
+                if (x < 0 || x >= a.Xin || j >= njx) continue;  // plane is padding: stage skipped on both sides
+                const int st = it % a.nstage;
+                mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+                const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                const CUtensorMap* map = seg2 ? &tmap2 : &tmap;
+                const int cgp = seg2 ? a.cg_plane2 : a.cg_plane;
+                const int cgi = b * (seg2 ? a.cg_batch2 : a.cg_batch) + c * 2;
+                if (!seg2) {
+                    mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + a.b_bytes);
+                    for (int i = 0; i < a.nbox; ++i) {
+                        const uint32_t dst = base + (uint32_t)a.boxes[i].dst16 * 16;
+                        const int zc = mz0 * a.sz + a.boxes[i].dz, yc = my0 * a.sy + a.boxes[i].dy;
+                        tma_load_5d(dst, map, full + st, 0, zc, yc, x, cgi);
+                        tma_load_5d(dst + a.a_plane, map, full + st, 0, zc, yc, x, cgi + cgp);
                     }
-                    const int px = x0 - 1 + s;
-                    if (px < 0 || px >= a.X) continue;  // whole plane is padding: nothing to stage
-                    const int st = it % a.SA;
-                    mbar_wait(a_empty + st, ((it / a.SA) & 1) ^ 1);
-                    mbar_expect_tx(a_full + st, 2 * a.a_box_bytes);
-                    uint8_t* dst = a_ring + (size_t)st * a.a_stage;
-                    const int cgi = b * a.cg_batch + c * 2;
-                    tma_load_5d(dst, &tmap, a_full + st, 0, z0 - hz, y0 - 1, px, cgi);
-                    tma_load_5d(dst + a.a_block, &tmap, a_full + st, 0, z0 - hz, y0 - 1, px, cgi + a.cg_plane);
-                    ++it;
+                    bulk_load(base + a.b_off, a.w + ((size_t)(sel * a.nchunk + c) * a.nj + j) * a.b_bytes, a.b_bytes,
+                              full + st);
+                } else {
+                    // shortcut source: same box shape, first box only (dy, dz of box 0), 1x1x1 weights
+                    mbar_expect_tx(full + st, 2 * a.box_tx + a.b2_bytes);
+                    const int zc = mz0 + a.dz2, yc = my0 + a.dy2;
+                    tma_load_5d(base, map, full + st, 0, zc, yc, x, cgi);
+                    tma_load_5d(base + a.a_plane, map, full + st, 0, zc, yc, x, cgi + cgp);
+                    bulk_load(base + a.b_off, a.w2 + ((size_t)ns * a.nchunk2 + c) * a.b2_bytes, a.b2_bytes, full + st);
                 }
+                ++it;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Cout >> 3) << 17) | (8u << 24);
-            uint32_t started = 0;  // bit per output line: accumulator already written
+        if (elect_one()) {
+            // ===== MMA issuer (one elected lane; every MMA accumulates into TMEM zeroed by the epilogue warps) =====
+            mbar_wait(tmem_zero, 0);
+            tc_fence_after();
             int it = 0;
-            for (int c = 0; c < nchunk; ++c) {
-                for (int s = 0; s < XT + 2; ++s) {
-                    const int px = x0 - 1 + s;
-                    const bool plane_ok = px >= 0 && px < a.X;
-                    uint32_t a_hi = 0, a_lo = 0;
-                    int st = 0;
-                    if (plane_ok) {
-                        st = it % a.SA;
-                        mbar_wait(a_full + st, (it / a.SA) & 1);
-                        a_hi = smem_u32(a_ring + (size_t)st * a.a_stage);
-                        a_lo = a_hi + a.a_block;
+            for (int s = 0; s < ntot; ++s) {
+                const bool seg2 = s >= nmain;
+                const int j = seg2 ? 0 : s % a.nj;
+                const int x = seg2 ? mx : mx * a.sx + j + a.xoff;
+                if (x < 0 || x >= a.Xin || j >= njx) continue;
+                const int st = it % a.nstage;
+                mbar_wait(full + st, (it / a.nstage) & 1);
+                tc_fence_after();
+                const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                const uint64_t da = make_desc(base, a.lbo_a, 128);
+                if (!seg2) {
+                    const uint64_t db = make_desc(base + a.b_off, a.lbo_b, 128);
+#pragma unroll 4
+                    for (int i = 0; i < a.nop; ++i) {
+                        const TcOp op = a.ops[i];
+                        umma_bf16(tmem_base + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
                     }
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int oxl = s - dx;  // local output x row fed by this plane through tap dx
-                        if (oxl < 0 || oxl >= XT) continue;
-                        if (oxl == 0) mbar_wait(b_full + dx, c & 1);  // first use of this slot in the slice
-                        tc_fence_after();
-                        if (plane_ok) {
-                            const uint32_t bs = smem_u32(b_ring + (size_t)dx * a.b_slot);
-                            for (int oy = 0; oy < YT; ++oy) {
-                                const int line = oxl * YT + oy;
-                                const uint32_t d_tmem = tmem_base + (uint32_t)(line * a.Cout);
-                                for (int dy = 0; dy < 3; ++dy) {
-                                    const int gy = y0 + oy + dy - 1;
-                                    if (gy < 0 || gy >= a.Y) continue;  // padding row
-                                    for (int dz = 0; dz < KZ; ++dz) {
-                                        const uint32_t aoff = (uint32_t)(oy + dy) * slab + (uint32_t)dz * 16;
-                                        const uint32_t boff = (uint32_t)(dy * KZ + dz) * b_tap;
-                                        const uint64_t dah = make_desc(a_hi + aoff, lbo_a, 128);
-                                        const uint64_t dal = make_desc(a_lo + aoff, lbo_a, 128);
-                                        const uint64_t dbh = make_desc(bs + boff, (uint32_t)a.Cout * 16, 128);
-                                        const uint64_t dbl = make_desc(bs + b_plane + boff, (uint32_t)a.Cout * 16, 128);
-                                        const uint32_t acc0 = (started >> line) & 1u;
-                                        umma_bf16(d_tmem, dah, dbh, idesc, acc0);
-                                        umma_bf16(d_tmem, dal, dbh, idesc, 1u);
-                                        umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-                                        started |= 1u << line;
-                                    }
-                                }
-                            }
-                        }
-                        if (oxl == XT - 1) umma_commit(b_empty + dx);  // last use of this weight slot
-                    }
-                    if (plane_ok) {
-                        umma_commit(a_empty + st);
-                        ++it;
+                } else {
+                    const uint64_t db = make_desc(base + a.b_off, a.lbo_b2, 128);
+                    for (int i = 0; i < a.nop2; ++i) {
+                        const TcOp op = a.ops2[i];
+                        umma_bf16(tmem_base + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
                     }
                 }
+                umma_commit(empty + st);
+                ++it;
             }
             umma_commit(acc_full);
         }
     } else {
-        // ===== epilogue: 4 warps, TMEM lanes (warp % 4) * 32 .. +31, thread = one z row =====
+        // ===== epilogue: 4 warps, TMEM lanes (warp % 4) * 32 .. +31, thread = one M-tile row =====
+        const int lane_base = (warp & 3) * 32;
+        {   // zero this warp's lanes of every accumulator column, then release the MMA issuer
+            const uint32_t used = (uint32_t)(a.nacc * (a.nchunk2 ? 2 : 1) * a.n_cta);
+            for (uint32_t c = 0; c < used; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)lane_base << 16) + c);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_zero);
+        }
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int lane_base = (warp & 3) * 32;
-        const int z = z0 + lane_base + lane;
+        const int r = lane_base + lane;
+        const int ly = r / a.LZ, zz = r % a.LZ;
+        const int Xo = a.out.X, Yo = a.out.Y, Zo = a.out.Z;
+        const int ox = mx * a.ux + px;
+        const int co0 = ns * a.n_cta;
+        const int nreal = min(a.n_cta, a.cout - co0);
+        const uint32_t sc_col = (uint32_t)(a.nacc * a.n_cta);  // shortcut accumulators follow the main ones
         __nv_bfloat16* out_hi = (__nv_bfloat16*)a.out.hi;
-        for (int line = 0; line < XT * YT; ++line) {
-            const int ox = x0 + line / YT, oy = y0 + line % YT;
+        for (int ai = 0; ai < a.nacc; ++ai) {
+            // rows of a partial (zero-padded) line group load their TMEM lane like everyone else
+            // (tcgen05.ld is warp-collective) but neither read the residual nor store
+            const bool valid = my0 + ly + (a.accs[ai].y_add / a.uy) < a.Ym;
+            const int oy = (my0 + ly) * a.uy + a.accs[ai].y_add;
+            const int oz = (mz0 + zz) * a.uz + a.accs[ai].z_add;
             float rsrc = 0.f;
-            if (a.res_mode == 2) rsrc = a.rsrc.ptr[b * a.rsrc.sb + ox * a.rsrc.sx + oy * a.rsrc.sy + z * a.rsrc.sz];
-            for (int c0 = 0; c0 < a.Cout; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(line * a.Cout + c0), r);
+            if (a.res_mode == 2 && valid) rsrc = a.rsrc.ptr[b * a.rsrc.sb + ox * a.rsrc.sx + oy * a.rsrc.sy + oz * a.rsrc.sz];
+            for (int c0 = 0; c0 < nreal; c0 += 16) {
+                uint32_t v[16], v2[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(ai * a.n_cta + c0);
+                tmem_ld16(taddr, v);
+                if (a.nchunk2) tmem_ld16(taddr + sc_col, v2);
                 tmem_ld_wait();
+                if (!valid) continue;
 #pragma unroll
                 for (int g8 = 0; g8 < 2; ++g8) {
-                    const int cc = c0 + g8 * 8;
+                    const int cc = co0 + c0 + g8 * 8;
+                    if (c0 + g8 * 8 >= nreal) break;
                     float o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float v = __uint_as_float(r[g8 * 8 + j]) * __ldg(a.ep.scale + cc + j) + __ldg(a.ep.shift + cc + j);
-                        o[j] = apply_act(v, a.ep.act, a.ep.slope);
+                    for (int q = 0; q < 8; ++q) {
+                        float f = __uint_as_float(v[g8 * 8 + q]) * __ldg(a.ep.scale + cc + q) + __ldg(a.ep.shift + cc + q);
+                        o[q] = apply_act(f, a.ep.act, a.ep.slope);
+                    }
+                    if (a.nchunk2) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o[q] += __uint_as_float(v2[g8 * 8 + q]) + __ldg(a.bias2 + cc + q);
                     }
                     if (a.res_mode == 1) {
                         const __nv_bfloat16* rp = (const __nv_bfloat16*)a.res.hi +
-                                                  act8_off(a.res.batch_stride, a.X, a.Y, a.Z, b, cc / 8, ox, oy, z);
+                                                  act8_off(a.res.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
                         float rr[8];
                         unpack8(ldg128(rp), ldg128(rp + a.res.lo_offset), rr);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] += rr[j];
+                        for (int q = 0; q < 8; ++q) o[q] += rr[q];
                     } else if (a.res_mode == 2) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] += __ldg(a.res_w + cc + j) * rsrc + __ldg(a.res_b + cc + j);
+                        for (int q = 0; q < 8; ++q) o[q] += __ldg(a.res_w + cc + q) * rsrc + __ldg(a.res_b + cc + q);
                     }
                     uint4 h, l;
                     pack8(o, h, l);
-                    __nv_bfloat16* p = out_hi + act8_off(a.out.batch_stride, a.X, a.Y, a.Z, b, cc / 8, ox, oy, z);
+                    __nv_bfloat16* p = out_hi + act8_off(a.out.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
                     *reinterpret_cast<uint4*>(p) = h;
                     *reinterpret_cast<uint4*>(p + a.out.lo_offset) = l;
                 }
@@ -302,94 +427,303 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-// Tile = as many output lines per CTA as TMEM (512 columns) and shared memory (>= 2 A stages next
-// to the 3 weight slots) allow, preferring 2x4, then 2x2, 1x2, 1x1.
-static bool plan_tile(const vsseg_act8* in, int cout, int kz, TcArgs* a) {
-    const int cand[4][2] = {{2, 4}, {2, 2}, {1, 2}, {1, 1}};
-    const int hz = kz == 3 ? 1 : 0, ZH = 128 + 2 * hz;
-    a->b_slot = (uint32_t)(2 * 3 * kz * cout * 32);
-    for (auto& c : cand) {
-        if (in->X % c[0] || in->Y % c[1]) continue;
-        if (c[0] * c[1] * cout > 512) continue;
-        const uint32_t box = (uint32_t)(2 * (c[1] + 2) * ZH * 16);
-        const uint32_t block = (box + 127) / 128 * 128;
-        const long budget = 227L * 1024 - 1024 - 3L * a->b_slot;
-        const int sa = (int)(budget / (2L * block));
-        if (sa < 2) continue;
-        a->XT = c[0];
-        a->YT = c[1];
-        a->a_box_bytes = box;
-        a->a_block = block;
-        a->a_stage = 2 * block;
-        a->SA = sa > 8 ? 8 : sa;
-        return true;
+// ---- host side: geometry -> tables ------------------------------------------------------------
+struct TcPlan {
+    TcArgs a;
+    cuuint32_t box[5], estr[5];
+    size_t smem;
+    unsigned grid;
+};
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct TcGeom {   // what gen_ops needs
+    bool tr, strided, line;
+    int KY, KZ, LY, LZ, BZ, npz, n_cta, sy;
+    uint32_t box_bytes, a_plane, b_plane;
+};
+
+// Elementary products (A view, weight tap, accumulator) of one stage, then merged: products that
+// read the SAME A view and write ADJACENT accumulators with ADJACENT weight rows become one
+// tcgen05.mma with a wider N.  In SS mode an MMA costs max(N/2, 32 + N/4) cycles (the 4 KB A read
+// from shared memory is the floor for N < 128, measured with tools/ubench/mma_rate.cu), so sharing the
+// A read between the (up to) three y taps that use it is worth up to 2.7x for the narrow layers.
+static bool gen_ops(const TcGeom& G, int YT, TcOp* ops, int* nop_out, TcAcc* accs, int* nacc_out) {
+    struct El { uint32_t a16; int tz, brow, col, n; };
+    El el[TC_MAX_ACC * 27];
+    int ne = 0, nacc = 0;
+    const int n = G.n_cta;
+    if (!G.tr) {
+        for (int y = 0; y < YT; ++y) {
+            accs[nacc].y_add = (int16_t)(y * G.LY);
+            accs[nacc].z_add = 0;
+            for (int dy = 0; dy < G.KY; ++dy)
+                for (int dz = 0; dz < G.KZ; ++dz) {
+                    uint32_t aoff;
+                    if (G.line) aoff = (uint32_t)(((y * G.sy + dy) * G.BZ + dz) * 16);
+                    else if (G.strided) aoff = (uint32_t)(dy * G.KZ + dz) * G.box_bytes + (uint32_t)y * 2048;
+                    else aoff = (uint32_t)dz * G.box_bytes + (uint32_t)((y * G.LY + dy) * G.LZ * 16);
+                    el[ne++] = {aoff / 16, dz, (G.KY - 1 - dy) * n, nacc * n, n};  // weight rows in reversed y order
+                }
+            ++nacc;
+        }
+    } else {
+        // phase p along an axis: p=0 -> (shift 0, tap 1); p=1 -> (shift 0, tap 2), (shift 1, tap 0).
+        // accumulator index = pz*(2*YT) + 2*y + py, so the phases fed by one A view are adjacent.
+        for (int pz = 0; pz < G.npz; ++pz)
+            for (int y = 0; y < YT; ++y)
+                for (int py = 0; py < 2; ++py) {
+                    const int ai = pz * 2 * YT + 2 * y + py;
+                    accs[ai].y_add = (int16_t)(y * G.LY * 2 + py);
+                    accs[ai].z_add = (int8_t)pz;
+                    for (int ddy = 0; ddy <= py; ++ddy)
+                        for (int ddz = 0; ddz <= pz; ++ddz) {
+                            const int ky = py == 0 ? 1 : (ddy == 0 ? 2 : 0);
+                            const int kz = G.npz == 1 ? 0 : (pz == 0 ? 1 : (ddz == 0 ? 2 : 0));
+                            const uint32_t aoff = G.line ? (uint32_t)((y + ddy) * G.BZ * 16)
+                                                         : (uint32_t)ddz * G.box_bytes + (uint32_t)((y * G.LY + ddy) * G.LZ * 16);
+                            el[ne++] = {aoff / 16, kz, ky * n, ai * n, n};
+                        }
+                    ++nacc;
+                }
     }
-    return false;
+    // merge: sort by (A view, weight z tap, column), then join runs
+    for (int i = 1; i < ne; ++i) {
+        El k = el[i];
+        int j = i - 1;
+        auto less = [](const El& p, const El& q) {
+            if (p.a16 != q.a16) return p.a16 < q.a16;
+            if (p.tz != q.tz) return p.tz < q.tz;
+            return p.col < q.col;
+        };
+        while (j >= 0 && less(k, el[j])) { el[j + 1] = el[j]; --j; }
+        el[j + 1] = k;
+    }
+    int nm = 0;
+    for (int i = 0; i < ne; ++i) {
+        if (nm && el[nm - 1].a16 == el[i].a16 && el[nm - 1].tz == el[i].tz && el[nm - 1].col + el[nm - 1].n == el[i].col &&
+            el[nm - 1].brow + el[nm - 1].n == el[i].brow && el[nm - 1].n + el[i].n <= 256)
+            el[nm - 1].n += el[i].n;
+        else
+            el[nm++] = el[i];
+    }
+    if (nm * 3 > TC_MAX_OPS) return false;
+    int nop = 0;
+    for (int i = 0; i < nm; ++i) {
+        const uint32_t b16 = (uint32_t)(el[i].tz * 2 * G.KY * n + el[i].brow);
+        for (int pass = 0; pass < 3; ++pass) {
+            TcOp& op = ops[nop++];
+            op.a16 = (uint16_t)(el[i].a16 + (pass == 1 ? G.a_plane / 16 : 0));
+            op.b16 = (uint16_t)(b16 + (pass == 2 ? G.b_plane / 16 : 0));
+            op.col = (uint16_t)el[i].col;
+            op.n8 = (uint16_t)(el[i].n / 8);
+        }
+    }
+    *nop_out = nop;
+    *nacc_out = nacc;
+    return true;
 }
 
-static bool tc_shape_ok(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g) {
-    if (!in || !out || !g) return false;
-    if (g->transposed || g->sx != 1 || g->sy != 1 || g->sz != 1) return false;
-    if (g->kx != 3 || g->ky != 3 || (g->kz != 1 && g->kz != 3)) return false;
-    if (in->C % 16 || out->C % 16 || out->C < 16 || out->C > 96) return false;
-    if (in->Z % 128 || in->X != out->X || in->Y != out->Y || in->Z != out->Z || in->B != out->B) return false;
+// Fills the plan for (in -> out, geometry, n_split); returns false when the shape is not covered
+// (the caller then uses the generic CUDA-core kernel).
+static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int n_split,
+                      const vsseg_act8* src2, TcPlan* P) {
+    if (!in || !out || !g || !in->hi || !out->hi) return false;
+    if (in->C % 16 || out->C % 8 || in->B != out->B || n_split < 1) return false;
+    const int KX = g->kx, KY = g->ky, KZ = g->kz;
+    if ((KX != 1 && KX != 3) || (KY != 1 && KY != 3) || (KZ != 1 && KZ != 3)) return false;
+    const bool tr = g->transposed != 0;
+    const bool strided = !tr && (g->sx != 1 || g->sy != 1 || g->sz != 1);
+    if (g->sx < 1 || g->sx > 2 || g->sy < 1 || g->sy > 2 || g->sz < 1 || g->sz > 2) return false;
+    // M grid
+    int Xm, Ym, Zm;
+    if (tr) {
+        // sub-pixel phases need k=3 on every stride-2 axis and k=1 on stride-1 axes; x and y strided
+        if (g->sx != 2 || g->sy != 2 || KX != 3 || KY != 3) return false;
+        if ((g->sz == 2) != (KZ == 3)) return false;
+        if (out->X != in->X * 2 || out->Y != in->Y * 2 || out->Z != in->Z * g->sz) return false;
+        Xm = in->X; Ym = in->Y; Zm = in->Z;
+    } else {
+        if (out->X != (in->X + g->sx - 1) / g->sx || out->Y != (in->Y + g->sy - 1) / g->sy ||
+            out->Z != (in->Z + g->sz - 1) / g->sz)
+            return false;
+        if (in->X % g->sx || in->Y % g->sy || in->Z % g->sz) return false;
+        Xm = out->X; Ym = out->Y; Zm = out->Z;
+    }
+    const int LZ = Zm >= 128 ? 128 : Zm;
+    if (Zm % LZ || 128 % LZ || LZ < 8) return false;
+    const int LY = 128 / LZ;
     const int64_t cgs = (int64_t)in->X * in->Y * in->Z * 8;
     if (in->lo_offset % cgs || in->batch_stride % cgs) return false;
-    TcArgs tmp{};
-    return plan_tile(in, out->C, g->kz, &tmp);
-}
-
-}  // namespace vsseg
-
-using namespace vsseg;
-
-extern "C" {
-
-int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g) {
-    return tc_shape_ok(in, out, g) ? 1 : 0;
-}
-
-int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, const void* w_packed,
-                    const vsseg_epilogue* ep, const vsseg_act8* res_act8, const vsseg_f32view* res_src,
-                    const float* res_w, const float* res_b, void* stream) {
-    VSSEG_REQUIRE(tc_shape_ok(in, out, g), "conv3d_tc: unsupported shape (need stride-1 3x3x{1,3}, Cin,Cout %% 16 == 0, "
-                                           "Cout <= 96, Z %% 128 == 0)");
-    VSSEG_REQUIRE(w_packed && ep && ep->scale && ep->shift, "conv3d_tc: NULL weights/epilogue");
-    VSSEG_REQUIRE(!(res_act8 && res_src), "conv3d_tc: at most one residual source");
-    TcArgs a{};
-    a.out = *out;
-    a.ep = *ep;
-    a.w = (const __nv_bfloat16*)w_packed;
-    a.Cin = in->C; a.Cout = out->C; a.X = in->X; a.Y = in->Y; a.Z = in->Z; a.B = in->B; a.KZ = g->kz;
-    if (res_act8) {
-        VSSEG_REQUIRE(res_act8->hi && res_act8->C == out->C && res_act8->X == out->X && res_act8->Y == out->Y &&
-                          res_act8->Z == out->Z && res_act8->B == out->B, "conv3d_tc: residual shape mismatch");
-        a.res_mode = 1;
-        a.res = *res_act8;
-    } else if (res_src) {
-        VSSEG_REQUIRE(res_src->ptr && res_w && res_b, "conv3d_tc: NULL cin1 residual");
-        a.res_mode = 2;
-        a.rsrc = *res_src; a.res_w = res_w; a.res_b = res_b;
+    if (src2) {
+        if (tr || strided) return false;
+        if (src2->C % 16 || src2->X != in->X || src2->Y != in->Y || src2->Z != in->Z || src2->B != in->B) return false;
+        if (src2->lo_offset % cgs || src2->batch_stride % cgs) return false;
     }
-    VSSEG_REQUIRE(plan_tile(in, a.Cout, a.KZ, &a), "conv3d_tc: tile does not fit in shared memory");
-    const int hz = a.KZ == 3 ? 1 : 0, ZH = 128 + 2 * hz;
-    const int cols = a.XT * a.YT * a.Cout;
-    a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    const int64_t cgs = (int64_t)in->X * in->Y * in->Z * 8;
+    const int cout_pad = round_up(out->C, 16);
+    if (cout_pad % n_split || (cout_pad / n_split) % 16) return false;
+    const int n_cta = cout_pad / n_split;
+    if (n_cta > 256) return false;
+
+    TcArgs& a = P->a;
+    memset(&a, 0, sizeof(a));
+    const int hz = KZ == 3 ? 1 : 0, hy = KY == 3 ? 1 : 0;
+    const int nphase = tr ? 2 * g->sz : 1;           // (py, pz) phases per CTA; px is a grid dimension
+    const int acc_mult = nphase * (src2 ? 2 : 1);
+    // flavour
+    // line mode: M tile = one z line; the stage holds BY whole input lines (pitch = 128 + 2*hz rows),
+    // every tap is an address offset (line, dz) into it.  Needs unit z stride.
+    const bool line = LY == 1 && g->sz == 1;
+    const int sy_in = tr ? 1 : g->sy;
+    // choose YT = number of y line groups per CTA
+    const int ygroups = (Ym + LY - 1) / LY;   // a partial last group is zero-filled by TMA and masked in the epilogue
+    const int stages_total = (tr ? (3 * (in->C / 16) + 1) / 2 : (in->C / 16) * KX) + (src2 ? src2->C / 16 : 0);
+    int best = 0;
+    double best_cost = 1e30;
+    size_t best_stage = 0;
+    int best_nstage = 0;
+    const int taps_stage = KY * KZ;
+    const uint32_t b_bytes = (uint32_t)(2 * taps_stage * n_cta * 32);
+    const long total_tiles_1 = (long)in->B * Xm * (Zm / LZ) * (tr ? 2 : 1) * n_split;
+    for (int YT = 1; YT <= ygroups && YT <= 16; ++YT) {
+        if (ygroups % YT) continue;
+        if (YT * acc_mult * n_cta > 512) break;
+        if (YT * acc_mult > TC_MAX_ACC) break;
+        int nbox, BY, BZ;
+        if (line) { nbox = 1; BY = tr ? YT + 1 : (YT - 1) * sy_in + KY; BZ = LZ + 2 * hz; }
+        else if (tr) { nbox = g->sz; BY = YT * LY + 1; BZ = LZ; }
+        else if (strided) { nbox = KY * KZ; BY = YT * LY; BZ = LZ; }
+        else { nbox = KZ; BY = YT * LY + 2 * hy; BZ = LZ; }
+        if (!line && (BY * (strided ? g->sy : 1) > 256 || BZ * (strided ? g->sz : 1) > 256)) break;
+        const size_t box_bytes = (size_t)2 * BY * BZ * 16;
+        const size_t a_plane = round_up((int)(nbox * box_bytes), 128);
+        double mma_cyc = 0;
+        {
+            TcGeom G{tr, strided, line, KY, KZ, LY, LZ, BZ, (int)g->sz, n_cta, sy_in, (uint32_t)box_bytes,
+                     (uint32_t)a_plane, b_bytes / 2};
+            static TcOp scratch[TC_MAX_OPS];
+            static TcAcc scratch_acc[TC_MAX_ACC];
+            int n1 = 0, n2 = 0;
+            if (!gen_ops(G, YT, scratch, &n1, scratch_acc, &n2) || (src2 && YT * 3 > TC_MAX_OPS2)) break;
+            for (int i = 0; i < n1; ++i) {   // SS-mode MMA cost, measured (tools/ubench/mma_rate.cu)
+                const double N = scratch[i].n8 * 8.0;
+                mma_cyc += N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
+            }
+        }
+        const size_t stage = 2 * a_plane + round_up((int)b_bytes, 128);
+        if (stage / 16 >= 16000) break;
+        const long budget = 227L * 1024 - 1024, half = 113L * 1024 - 1024;
+        int nst = (int)(budget / (long)stage);
+        if (nst < 2) break;
+        // cost model: tiles per SM x (stages x max(MMA time, smem fill time at ~32 B/cycle/SM) + a fixed
+        // prologue/epilogue cost that a second co-resident CTA mostly hides)
+        const long tiles = total_tiles_1 * (ygroups / YT);
+        const bool two = 2 * (long)stage <= half && YT * acc_mult * n_cta <= 256;
+        const double fill_cyc = (double)stage / 32.0;
+        const double stage_cyc = mma_cyc > fill_cyc ? mma_cyc : fill_cyc;
+        const double tile_cyc = stages_total * stage_cyc + (two ? 1500.0 : 5000.0);
+        const double cost = (double)((tiles + 147) / 148) * tile_cyc;
+        if (cost < best_cost) {
+            best_cost = cost; best = YT; best_stage = stage;
+            best_nstage = two ? (int)(half / (long)stage) : nst;
+            if (best_nstage > 4) best_nstage = 4;
+        }
+    }
+    if (!best) return false;
+    const int YT = best;
+    int nbox, BY, BZ;
+    if (line) { nbox = 1; BY = tr ? YT + 1 : (YT - 1) * sy_in + KY; BZ = LZ + 2 * hz; }
+    else if (tr) { nbox = g->sz; BY = YT * LY + 1; BZ = LZ; }
+    else if (strided) { nbox = KY * KZ; BY = YT * LY; BZ = LZ; }
+    else { nbox = KZ; BY = YT * LY + 2 * hy; BZ = LZ; }
+    const uint32_t box_bytes = (uint32_t)(2 * BY * BZ * 16);
+    a.out = *out;
+    a.nchunk = in->C / 16;
+    a.nj = tr ? 2 : KX;   // transposed: px=0 CTAs use j=0 only (see nj_eff below)
+    a.nchunk2 = src2 ? src2->C / 16 : 0;
+    a.nbox = nbox;
+    a.nstage = best_nstage;
+    a.a_plane = (uint32_t)round_up((int)(nbox * box_bytes), 128);
+    a.b_off = 2 * a.a_plane;
+    a.b_bytes = b_bytes;
+    a.b_plane = b_bytes / 2;
+    a.b2_bytes = (uint32_t)(2 * n_cta * 32);
+    a.b2_plane = a.b2_bytes / 2;
+    a.stage_bytes = (uint32_t)best_stage;
+    a.box_tx = box_bytes;
+    a.lbo_a = (uint32_t)(BY * BZ * 16);
+    a.lbo_b = (uint32_t)(KY * n_cta * 16);   // B region: [tz][khalf][ty'][n][8]
+    a.lbo_b2 = (uint32_t)(n_cta * 16);
+    const TcGeom G{tr, strided, line, KY, KZ, LY, LZ, BZ, (int)g->sz, n_cta, sy_in, box_bytes, a.a_plane, a.b_plane};
+    a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);   // N field (bits 17..22) comes from the op
+    a.ntz = Zm / LZ; a.nty = ygroups / YT; a.ntx = Xm;
+    a.npx = tr ? 2 : 1; a.nsplit = n_split; a.nsel = a.npx * n_split;
+    a.LZ = LZ; a.LY = LY; a.YL = YT * LY; a.Ym = Ym;
+    a.n_cta = n_cta; a.cout = out->C;
+    a.sx = tr ? 1 : g->sx; a.sy = tr ? 1 : g->sy; a.sz = tr ? 1 : g->sz;
+    a.xoff = tr ? 0 : -(KX / 2);
+    a.Xin = in->X;
     a.cg_plane = (int)(in->lo_offset / cgs);
     a.cg_batch = (int)(in->batch_stride / cgs);
+    if (src2) {
+        a.cg_plane2 = (int)(src2->lo_offset / cgs);
+        a.cg_batch2 = (int)(src2->batch_stride / cgs);
+    }
+    a.ux = tr ? 2 : 1; a.uy = tr ? 2 : 1; a.uz = tr ? g->sz : 1;
+    a.line_mode = line ? 1 : 0;
+    a.BY = BY; a.pitch = BZ; a.hy = tr ? 0 : hy; a.hz = hz; a.Yin = in->Y; a.Zin = in->Z;
+    a.in = *in;
+    if (src2) a.in2 = *src2;
+    // boxes
+    for (int i = 0; i < nbox; ++i) {
+        TcBox& bx = a.boxes[i];
+        bx.dst16 = (uint16_t)((size_t)i * box_bytes / 16);
+        if (tr) { bx.dy = 0; bx.dz = (int8_t)i; }
+        else if (strided) { bx.dy = (int8_t)(i / KZ - hy); bx.dz = (int8_t)(i % KZ - hz); }
+        else { bx.dy = (int8_t)-hy; bx.dz = (int8_t)(i - hz); }
+    }
+    // accumulators + ops
+    int nacc = 0, nop = 0;
+    if (!gen_ops(G, YT, a.ops, &nop, a.accs, &nacc)) return false;
+    a.nacc = nacc;
+    a.nop = nop;
+    if (src2) {
+        int n2 = 0;
+        for (int y = 0; y < YT; ++y) {
+            uint32_t aoff;
+            // the shortcut source is staged with the main box shape: the centre sits at (+hy, +hz)
+            if (line) aoff = (uint32_t)(((y + hy) * BZ + hz) * 16);
+            else aoff = (uint32_t)((y * LY + hy) * LZ * 16);   // staged unshifted in z (dz2 = 0)
+            for (int pass = 0; pass < 3; ++pass) {
+                TcOp& op = a.ops2[n2++];
+                op.a16 = (uint16_t)(aoff / 16 + (pass == 1 ? a.a_plane / 16 : 0));
+                op.b16 = (uint16_t)(pass == 2 ? a.b2_plane / 16 : 0);
+                op.col = (uint16_t)((nacc + y) * n_cta);
+                op.n8 = (uint16_t)(n_cta / 8);
+            }
+        }
+        a.nop2 = n2;
+        a.dy2 = -hy;
+        a.dz2 = 0;
+    }
+    const int cols = nacc * (src2 ? 2 : 1) * n_cta;
+    a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    P->box[0] = 8; P->box[1] = (cuuint32_t)(BZ * (strided ? g->sz : 1)); P->box[2] = (cuuint32_t)(BY * (strided ? g->sy : 1));
+    P->box[3] = 1; P->box[4] = 2;
+    P->estr[0] = 1; P->estr[1] = (cuuint32_t)(strided ? g->sz : 1); P->estr[2] = (cuuint32_t)(strided ? g->sy : 1);
+    P->estr[3] = 1; P->estr[4] = 1;
+    P->smem = 1024 + (size_t)a.nstage * a.stage_bytes;
+    P->grid = (unsigned)((long)in->B * a.ntx * a.nty * a.ntz * a.nsel);
+    return true;
+}
 
-    CUtensorMap tmap;
-    const cuuint64_t gdim[5] = {8, (cuuint64_t)in->Z, (cuuint64_t)in->Y, (cuuint64_t)in->X,
-                                (cuuint64_t)(a.cg_plane + (in->B - 1) * a.cg_batch + in->C / 8)};
-    const cuuint64_t gstr[4] = {16, (cuuint64_t)in->Z * 16, (cuuint64_t)in->Y * in->Z * 16, (cuuint64_t)cgs * 2};
-    const cuuint32_t box[5] = {8, (cuuint32_t)ZH, (cuuint32_t)(a.YT + 2), 1, 2};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map(CUtensorMap* tmap, const vsseg_act8* t, int cg_plane, int cg_batch, const TcPlan& P) {
     // the driver entry point is resolved through the runtime so the library has no link-time
     // dependency on libcuda.so (it must load on a GPU-less build box)
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -401,14 +735,113 @@ int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_con
         }
         encode = (EncodeFn)fn;
     }
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, in->hi, gdim, gstr, box, estr,
+    const int64_t cgs = (int64_t)t->X * t->Y * t->Z * 8;
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)t->Z, (cuuint64_t)t->Y, (cuuint64_t)t->X,
+                                (cuuint64_t)(cg_plane + (t->B - 1) * cg_batch + t->C / 8)};
+    const cuuint64_t gstr[4] = {16, (cuuint64_t)t->Z * 16, (cuuint64_t)t->Y * t->Z * 16, (cuuint64_t)cgs * 2};
+    CUresult cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t->hi, gdim, gstr, P.box, P.estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         set_error("conv3d_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         return (int)cr;
     }
-    const size_t smem = 1024 + (size_t)a.SA * a.a_stage + 3 * (size_t)a.b_slot;
+    return 0;
+}
+
+}  // namespace vsseg
+
+using namespace vsseg;
+
+extern "C" {
+
+int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int32_t n_split,
+                              const vsseg_act8* shortcut_src) {
+    TcPlan P;
+    return make_plan(in, out, g, n_split, shortcut_src, &P) ? 1 : 0;
+}
+
+int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
+                                  const vsseg_act8* shortcut_src) {
+    static TcPlan P;
+    if (!make_plan(in, out, g, 1, shortcut_src, &P)) {
+        // a full-width N may not fit TMEM next to a shortcut accumulator: try the finest split
+        const int n16 = out ? (out->C + 15) / 16 : 0;
+        for (int s = 2; s <= n16; ++s)
+            if (n16 % s == 0 && make_plan(in, out, g, s, shortcut_src, &P)) return s;
+        return 0;
+    }
+    const long tiles = (long)P.grid;
+    const int n16 = (out->C + 15) / 16;
+    int best = 1;
+    for (int s = 1; s <= n16; ++s) {
+        if (n16 % s) continue;
+        if (!make_plan(in, out, g, s, shortcut_src, &P)) continue;
+        best = s;
+        if ((long)P.grid >= 120 || tiles * s >= 120) break;
+    }
+    return best;
+}
+
+int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int32_t n_split,
+                             const vsseg_act8* shortcut_src, char* buf, int32_t buflen) {
+    static TcPlan P;
+    VSSEG_REQUIRE(buf && buflen > 0, "conv3d_tc_describe: no buffer");
+    if (!make_plan(in, out, g, n_split, shortcut_src, &P)) {
+        snprintf(buf, buflen, "unsupported");
+        return 0;
+    }
+    const TcArgs& a = P.a;
+    int n = snprintf(buf, buflen,
+                     "grid=%u smem=%zu nstage=%d stage_bytes=%u line_mode=%d LZ=%d LY=%d YL=%d BY=%d pitch=%d nbox=%d "
+                     "box=[%u,%u,%u,%u,%u] estr=[%u,%u] box_tx=%u a_plane=%u b_off=%u b_bytes=%u lbo_a=%u lbo_b=%u nacc=%d "
+                     "n_cta=%d tmem_cols=%u nchunk=%d nj=%d nchunk2=%d nop=%d nop2=%d ntx=%d nty=%d ntz=%d nsel=%d ops:",
+                     P.grid, P.smem, a.nstage, a.stage_bytes, a.line_mode, a.LZ, a.LY, a.YL, a.BY, a.pitch, a.nbox, P.box[0],
+                     P.box[1], P.box[2], P.box[3], P.box[4], P.estr[1], P.estr[2], a.box_tx, a.a_plane, a.b_off, a.b_bytes,
+                     a.lbo_a, a.lbo_b, a.nacc, a.n_cta, a.tmem_cols, a.nchunk, a.nj, a.nchunk2, a.nop, a.nop2, a.ntx, a.nty,
+                     a.ntz, a.nsel);
+    for (int i = 0; i < a.nop && n < buflen - 40; ++i)
+        n += snprintf(buf + n, buflen - n, " (a%u b%u c%u n%u)", a.ops[i].a16, a.ops[i].b16, a.ops[i].col, a.ops[i].n8 * 8);
+    return 0;
+}
+
+int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, const void* w_packed,
+                    int32_t n_split, const vsseg_epilogue* ep, const vsseg_act8* res_act8, const vsseg_f32view* res_src,
+                    const float* res_w, const float* res_b, const vsseg_act8* shortcut_src, const void* shortcut_w,
+                    const float* shortcut_bias, void* stream) {
+    static TcPlan P;  // 2.5 KB of tables: kept off the stack; calls are serialised by the host thread
+    VSSEG_REQUIRE(make_plan(in, out, g, n_split, shortcut_src, &P),
+                  "conv3d_tc: unsupported shape (see vsseg_conv3d_tc_supported)");
+    VSSEG_REQUIRE(w_packed && ep && ep->scale && ep->shift, "conv3d_tc: NULL weights/epilogue");
+    VSSEG_REQUIRE(!(res_act8 && res_src), "conv3d_tc: at most one residual source");
+    VSSEG_REQUIRE(!shortcut_src || (shortcut_w && shortcut_bias), "conv3d_tc: shortcut needs weights and bias");
+    TcArgs& a = P.a;
+    a.ep = *ep;
+    a.w = (const uint8_t*)w_packed;
+    a.w2 = (const uint8_t*)shortcut_w;
+    a.bias2 = shortcut_bias;
+    if (res_act8) {
+        VSSEG_REQUIRE(res_act8->hi && res_act8->C == out->C && res_act8->X == out->X && res_act8->Y == out->Y &&
+                          res_act8->Z == out->Z && res_act8->B == out->B, "conv3d_tc: residual shape mismatch");
+        a.res_mode = 1;
+        a.res = *res_act8;
+    } else if (res_src) {
+        VSSEG_REQUIRE(res_src->ptr && res_w && res_b, "conv3d_tc: NULL cin1 residual");
+        a.res_mode = 2;
+        a.rsrc = *res_src; a.res_w = res_w; a.res_b = res_b;
+    }
+    CUtensorMap tmap, tmap2;
+    if (a.line_mode) {  // staged with plain bulk copies: no tensor map needed
+        memset(&tmap, 0, sizeof(tmap));
+        tmap2 = tmap;
+    } else {
+        if (int e = encode_map(&tmap, in, a.cg_plane, a.cg_batch, P)) return e;
+        if (shortcut_src) {
+            if (int e = encode_map(&tmap2, shortcut_src, a.cg_plane2, a.cg_batch2, P)) return e;  // never strided
+        } else {
+            tmap2 = tmap;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -418,8 +851,7 @@ int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_con
         }
         attr_set = true;
     }
-    const unsigned grid = (unsigned)((in->X / a.XT) * (in->Y / a.YT) * (in->Z / 128) * in->B);
-    conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmap, a);
+    conv_tc_kernel<<<P.grid, TC_THREADS, P.smem, (cudaStream_t)stream>>>(tmap, tmap2, a);
     return check_launch("conv3d_tc");
 }
 

@@ -43,17 +43,39 @@ def pack_conv_weight(w: torch.Tensor, transposed: bool, cout_pad: int | None = N
     return p.contiguous()
 
 
-def pack_conv_weight_tc(w: torch.Tensor) -> torch.Tensor:
-    """Conv3d weight [Cout,Cin,3,3,KZ] -> bf16 [Cin/16][dx][plane hi/lo][dy][dz][khalf][Cout][8]
-    (the shared-memory image vsseg_conv3d_tc streams with cp.async.bulk; include/vsseg_b200.h)."""
-    cout, cin, kx, ky, kz = w.shape
+def _split_planes(w: torch.Tensor) -> torch.Tensor:
     w = w.float()
     hi = w.bfloat16()
     lo = (w - hi.float()).bfloat16()
-    p = torch.stack([hi, lo])  # [plane, Cout, Cin, dx, dy, dz]
-    p = p.reshape(2, cout, cin // 16, 2, 8, kx, ky, kz)  # Cin -> (c16, khalf, j)
-    p = p.permute(2, 5, 0, 6, 7, 3, 1, 4)  # [c16, dx, plane, dy, dz, khalf, Cout, j]
-    return p.contiguous()
+    return torch.stack([hi, lo])
+
+
+def pack_conv_weight_tc(w: torch.Tensor, transposed: bool = False, n_split: int = 1, _flip_y: bool = True) -> torch.Tensor:
+    """torch conv weight -> bf16 [sel][Cin/16][j][plane hi/lo][tz][khalf][ty'][n_cta][8], the shared-memory
+    image vsseg_conv3d_tc streams with cp.async.bulk (layout documented in include/vsseg_b200.h).
+    ty' = ky-1-ty for Conv3d (so the y taps that share an input line are adjacent N rows), ty for
+    ConvTranspose3d."""
+    if transposed:  # ConvTranspose3d [Cin, Cout, kx, ky, kz] -> per output-x parity px, input-x shift j
+        wt = w.permute(1, 0, 2, 3, 4)
+        z = torch.zeros_like(wt[:, :, 0])
+        per_px = [torch.stack([wt[:, :, 1], z], 2), torch.stack([wt[:, :, 2], wt[:, :, 0]], 2)]
+        return torch.cat([pack_conv_weight_tc(q, False, n_split, _flip_y=False) for q in per_px]).contiguous()
+    cout, cin, kx, ky, kz = w.shape
+    cp = _round_up(cout, 16)
+    if cp % n_split or (cp // n_split) % 16 or cin % 16:
+        raise ValueError("pack_conv_weight_tc: Cin % 16, round_up(Cout,16) % (16*n_split) must be 0")
+    if cp != cout:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, 0, 0, cp - cout))
+    n_cta = cp // n_split
+    if _flip_y:
+        w = w.flip(3)
+    p = _split_planes(w).reshape(2, n_split, n_cta, cin // 16, 2, 8, kx, ky, kz)  # plane sel n c khalf e j ty tz
+    return p.permute(1, 3, 6, 0, 8, 4, 7, 2, 5).contiguous()  # sel c j plane tz khalf ty' n e
+
+
+def pack_shortcut_weight_tc(w: torch.Tensor, n_split: int = 1) -> torch.Tensor:
+    """1x1x1 shortcut Conv3d weight [Cout, Csrc, 1,1,1] -> bf16 [n-slice][Csrc/16][plane][khalf][n_cta][8]."""
+    return pack_conv_weight_tc(w, False, n_split).reshape(n_split, w.shape[1] // 16, 2, 2, -1, 8).contiguous()
 
 
 def tc_enabled() -> bool:
@@ -163,8 +185,10 @@ class UNetEvalPlan:
         return b
 
     def _add_conv(self, name, p, src, dst, k, stride=(1, 1, 1), transposed=False, norm=True, act="prelu",
-                  res=None, res_cin1=None):
-        """src/dst: Act8 views.  One fused Convolution block (+ optional residual)."""
+                  res=None, res_cin1=None, shortcut=None):
+        """src/dst: Act8 views.  One fused Convolution block (+ optional residual).
+        shortcut = (prefix of the 1x1x1 residual conv, its Act8 source): fused as a second accumulator
+        on the tensor-core path; returns False if it could not be fused (caller adds it separately)."""
         cout = dst.C
         cpad = _round_up(cout, 16)
         scale, shift, slope, code = fold_epilogue(self.sd, p, cout, cpad, norm, act)
@@ -177,14 +201,32 @@ class UNetEvalPlan:
         self._keep += [src, dst, g, ep, res]
         extra = _nvox(dst) * cout if res is not None else (_nvox(dst) if res_cin1 is not None else 0)
         fl, nb = _conv_cost(src, dst, k, transposed, src.C, cout, extra)
-        if self.use_tc and self.lib.vsseg_conv3d_tc_supported(C.byref(src), C.byref(dst), C.byref(g)):
-            w = self._dev(pack_conv_weight_tc(self.sd[p + "conv.weight"]))
-            args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), C.byref(ep)) + tail
-            self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc, args, fl, nb, kind="tcgen05"))
-            return
+        if self.use_tc and src.C % 16 == 0:
+            sc_src = shortcut[1] if shortcut is not None else None
+            sc_p = C.byref(sc_src) if sc_src is not None else None
+            ns = self.lib.vsseg_conv3d_tc_suggest_split(C.byref(src), C.byref(dst), C.byref(g), sc_p)
+            fused = ns > 0 and shortcut is not None
+            if ns == 0 and shortcut is not None:
+                sc_p = None
+                ns = self.lib.vsseg_conv3d_tc_suggest_split(C.byref(src), C.byref(dst), C.byref(g), None)
+            if ns > 0:
+                w = self._dev(pack_conv_weight_tc(self.sd[p + "conv.weight"], transposed, ns))
+                sc_tail = (None, None, None)
+                if fused:
+                    q = shortcut[0]
+                    w2 = self._dev(pack_shortcut_weight_tc(self.sd[q + "weight"], ns))
+                    b2 = self._dev(torch.nn.functional.pad(self.sd[q + "bias"].float(), (0, cpad - cout)))
+                    sc_tail = (sc_p, w2.data_ptr(), b2.data_ptr())
+                    self._keep.append(sc_src)
+                    f2, n2 = _conv_cost(sc_src, dst, (1, 1, 1), False, sc_src.C, cout)
+                    fl, nb = fl + f2, nb + n2 - 4 * _nvox(dst) * cout
+                args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), ns, C.byref(ep)) + tail + sc_tail
+                self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc, args, fl, nb, kind="tcgen05"))
+                return fused
         w = self._dev(pack_conv_weight(self.sd[p + "conv.weight"], transposed, cpad))
         args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep)) + tail
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
+        return False
 
     def _add_shortcut(self, name, p, src, dst):
         """1x1x1 shortcut conv of a ResidualUnit (convolutions.py:241-250) -> addend buffer."""
@@ -220,16 +262,23 @@ class UNetEvalPlan:
         self._keep += [src, h, av, g]
 
     def _add_ru(self, name, p, src, h_buf, r_buf, dst, k, subunits):
-        """ResidualUnit with `subunits` Convolution blocks and a 1x1x1 shortcut; src/dst act8 views."""
+        """ResidualUnit with `subunits` Convolution blocks and a 1x1x1 shortcut; src/dst act8 views.
+        The shortcut is a second accumulator of the last conv when the tensor-core path covers it,
+        else a separate launch into the addend buffer r_buf."""
         cout = dst.C
+        sc = (p + "residual.", src)
+        last = p + f"conv.unit{subunits - 1}."
+        last_src = src if subunits == 1 else h_buf.view(0, cout)
+        if subunits == 2:
+            self._add_conv(name + ".unit0", p + "conv.unit0.", src, last_src, k)
+        n0 = len(self.steps)
+        if self._add_conv(name + f".unit{subunits - 1}", last, last_src, dst, k, shortcut=sc):
+            return
+        # not fused: drop the step just added and redo it with an explicit shortcut launch
+        del self.steps[n0:]
         r = r_buf.view(0, cout)
         self._add_shortcut(name + ".residual", p + "residual.", src, r)
-        if subunits == 1:
-            self._add_conv(name + ".unit0", p + "conv.unit0.", src, dst, k, res=r)
-        else:
-            h = h_buf.view(0, cout)
-            self._add_conv(name + ".unit0", p + "conv.unit0.", src, h, k)
-            self._add_conv(name + ".unit1", p + "conv.unit1.", h, dst, k, res=r)
+        self._add_conv(name + f".unit{subunits - 1}", last, last_src, dst, k, res=r)
 
     # -- plan ---------------------------------------------------------------------------
     def _build(self):
@@ -373,11 +422,15 @@ class UNetEvalPlan:
         return out, list(self.att_maps)
 
 
-def conv_block_ncdhw(x, sd, kernel_size, stride, transposed, norm, act, residual=None):
+def conv_block_ncdhw(x, sd, kernel_size, stride, transposed, norm, act, residual=None, shortcut=None,
+                     require_tc=False):
     """One fused Convolution block on an NCDHW fp32 CUDA tensor (standalone-module path).
 
     sd holds conv.weight / conv.bias (/ norm.* / act.weight).  Channels are zero-padded to the
     act8 granularity (8 in, 16 out) so any channel count works; pack and unpack are native kernels.
+    shortcut = (x_src NCDHW, weight [Cout,Csrc,1,1,1], bias [Cout]) fuses a 1x1x1 shortcut conv as a
+    second accumulator (tensor-core path only).  require_tc raises if the tcgen05 path does not cover
+    the shape (used by the tests to prove which kernel ran).
     """
     lib = _lib.load()
     if not x.is_cuda:
@@ -413,11 +466,26 @@ def conv_block_ncdhw(x, sd, kernel_size, stride, transposed, norm, act, residual
     sv, dv = src.view(), dst.view()
     stream = torch.cuda.current_stream(x.device).cuda_stream
     res_p = C.byref(res_v) if res_v is not None else None
-    if tc_enabled() and cin8 == cin and cout16 == cout and lib.vsseg_conv3d_tc_supported(
-            C.byref(sv), C.byref(dv), C.byref(g)):
-        wt = pack_conv_weight_tc(w0)
-        _lib.check(lib.vsseg_conv3d_tc(C.byref(sv), C.byref(dv), C.byref(g), wt.data_ptr(), C.byref(ep), res_p,
-                                       None, None, None, stream), "conv3d_tc")
+    ns = 0
+    sc_v = None
+    if shortcut is not None:
+        xs, ws, bs = shortcut
+        sbuf = Act8Buffer(B, xs.shape[1], *xs.shape[2:], x.device).from_ncdhw(xs.float())
+        sc_v = sbuf.view()
+    if tc_enabled() and cin8 == cin and cin % 16 == 0:
+        ns = lib.vsseg_conv3d_tc_suggest_split(C.byref(sv), C.byref(dv), C.byref(g),
+                                               C.byref(sc_v) if sc_v is not None else None)
+    if (require_tc or shortcut is not None) and ns <= 0:
+        raise _lib.NativeLibraryError("the tcgen05 path does not cover this shape")
+    if ns > 0:
+        wt = pack_conv_weight_tc(w0, transposed, ns)
+        sc_tail = (None, None, None)
+        if shortcut is not None:
+            w2 = pack_shortcut_weight_tc(ws, ns)
+            b2 = torch.nn.functional.pad(bs.float(), (0, cout16 - cout)).contiguous()
+            sc_tail = (C.byref(sc_v), w2.data_ptr(), b2.data_ptr())
+        _lib.check(lib.vsseg_conv3d_tc(C.byref(sv), C.byref(dv), C.byref(g), wt.data_ptr(), ns, C.byref(ep), res_p,
+                                       None, None, None, *sc_tail, stream), "conv3d_tc")
     else:
         _lib.check(lib.vsseg_conv3d_act8(C.byref(sv), C.byref(dv), C.byref(g), w.data_ptr(), cout16, C.byref(ep),
                                          res_p, None, None, None, stream), "conv3d_act8")
