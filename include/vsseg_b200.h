@@ -119,6 +119,15 @@ int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const
                               int32_t n_split, const vsseg_act8* shortcut_src);
 int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
                                   const vsseg_act8* shortcut_src);
+/* Tensor-core conv with 1..16 output channels written as planar fp32 (attention conv2 + Sigmoid,
+ * reference attentionblock.py:21-30; the top ResidualUnit's conv_only unit with its 1x1x1 shortcut
+ * folded into the centre tap, unet2d5_spvPA.py:186-190).  Same contract as vsseg_conv3d_smallcout:
+ * with sw_weight the result is blended into `out` (out += sw_weight[v] * y, MONAI
+ * sliding_window_inference step 6, reference call site VSparams.py:568-574).
+ * w_packed: as vsseg_conv3d_tc with n_split = 1 and Cout zero-padded to 16; ep->scale/shift: [16]. */
+int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g,
+                           const void* w_packed, const vsseg_epilogue* ep, const float* sw_weight, void* stream);
+
 /* Human-readable description of the launch plan (tile, stages, op table) for tests and DESIGN.md. */
 int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
                              int32_t n_split, const vsseg_act8* shortcut_src, char* buf, int32_t buflen);

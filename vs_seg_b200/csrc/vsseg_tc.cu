@@ -55,6 +55,20 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// box load through either map flavour: "wide" maps merge (z, 8 channels) into one dimension of 8-byte
+// elements so a box row is a whole z line (TMA fetches a 16-byte-row box ~4x slower)
+__device__ __forceinline__ void tma_box(int wide, uint32_t dst, const CUtensorMap* map, uint64_t* bar, int z, int y, int x,
+                                        int cg) {
+    if (wide) tma_load_4d(dst, map, bar, z * 2, y, x, cg);
+    else tma_load_5d(dst, map, bar, 0, z, y, x, cg);
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -166,7 +180,7 @@ struct TcArgs {
     uint32_t box_tx, b_bytes, b2_bytes, b2_plane;   // bytes of one box (one plane), of the weight slices
     uint32_t lbo_a, lbo_b, lbo_b2, idesc, tmem_cols;
     // tile decomposition of the M grid
-    int ntz, nty, ntx, nsel, npx, nsplit;
+    int ntz, nty, ntx, nsel, npx, nsplit, ntiles, nbuf;
     int LZ, LY, YL, Ym;      // M-tile shape, y lines of the M grid per CTA tile, y extent of the M grid
     int n_cta;               // output channels per CTA (multiple of 16), n_real: channels to store
     int cout;                // real Cout (multiple of 8)
@@ -178,7 +192,10 @@ struct TcArgs {
     int ux, uy, uz;
     int dy2, dz2;            // box origin shift of the shortcut source
     // line mode (M tile = one z line of 128): A staged by per-line bulk copies instead of tensor-map boxes
-    int line_mode, BY, pitch, hy, hz, Yin, Zin;
+    int line_mode, map_wide, BY, pitch, hy, hz, Yin, Zin;
+    int out_mode;            // 0: act8 output, 1: planar fp32 output (Cout <= 16) with optional sliding-window blend
+    vsseg_f32view outf;
+    const float* sw_weight;
     vsseg_act8 in, in2;
     TcOp ops[TC_MAX_OPS];
     TcOp ops2[TC_MAX_OPS2];
@@ -186,39 +203,57 @@ struct TcArgs {
     TcAcc accs[TC_MAX_ACC];
 };
 
-constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
+constexpr int TC_THREADS = 192;  // warp 0: producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
+__device__ uint4 g_zero_line[136];  // source of padding lines / halo rows for the bulk-copy producer (zero-initialised)
+
+struct TcTile {
+    int sel, tz, ty, mx, b, px, ns, my0, mz0, njx;
+};
+__device__ __forceinline__ TcTile decode_tile(const TcArgs& a, int t) {
+    TcTile T;
+    T.sel = t % a.nsel; t /= a.nsel;
+    T.tz = t % a.ntz; t /= a.ntz;
+    T.ty = t % a.nty; t /= a.nty;
+    T.mx = t % a.ntx; t /= a.ntx;
+    T.b = t;
+    T.px = T.sel / a.nsplit; T.ns = T.sel % a.nsplit;
+    T.my0 = T.ty * a.YL; T.mz0 = T.tz * a.LZ;
+    T.njx = (a.npx == 2 && T.px == 0) ? 1 : a.nj;  // transposed conv, even x phase: only the centre x tap
+    return T;
+}
+
+// Persistent kernel: CTA i walks tiles i, i+gridDim.x, ...  The shared-memory ring runs across tile
+// boundaries (the producer prefetches the next tile during the MMAs/epilogue of the current one) and
+// the accumulators are double-buffered in TMEM when two tiles fit (nbuf = 2), so the epilogue of tile
+// k overlaps the main loop of tile k+1.
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ CUtensorMap tmap2,
                                                              const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [nstage]
     uint64_t* empty = full + 8;                          // [nstage]
-    uint64_t* acc_full = full + 16;
-    uint64_t* tmem_zero = full + 17;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 18);
-    const uint32_t ring = smem_u32(smem) + 1024;
+    uint64_t* acc_full = full + 16;                      // [2]
+    uint64_t* acc_empty = full + 18;                     // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 20);
+    // per-channel epilogue constants of this CTA's Cout slice(s), staged once: [scale | shift | bias2 | res_w | res_b][256]
+    float* ep_c = reinterpret_cast<float*>(smem + 1024);
+    const uint32_t ring = smem_u32(smem) + TC_HDR;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
-    int t = blockIdx.x;
-    const int sel = t % a.nsel; t /= a.nsel;
-    const int tz = t % a.ntz; t /= a.ntz;
-    const int ty = t % a.nty; t /= a.nty;
-    const int mx = t % a.ntx; t /= a.ntx;
-    const int b = t;
-    const int px = sel / a.nsplit, ns = sel % a.nsplit;
-    const int my0 = ty * a.YL, mz0 = tz * a.LZ;
     const int nmain = a.nchunk * a.nj, ntot = nmain + a.nchunk2;
-    const int njx = (a.npx == 2 && px == 0) ? 1 : a.nj;  // transposed conv, even x phase: only the centre x tap
+    const uint32_t buf_cols = (uint32_t)(a.nacc * (a.nchunk2 ? 2 : 1) * a.n_cta);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.nstage; ++i) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, 1);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(tmem_zero, 4);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(acc_full + i, 1);
+            mbar_init(acc_empty + i, 4);
+        }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0 && !a.line_mode) {
@@ -226,15 +261,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         if (a.nchunk2) prefetch_tmap(&tmap2);
     }
     if (warp == 1) tmem_alloc(tmem_ptr, a.tmem_cols);
-    if (a.line_mode) {
-        // padding lines / halo rows of the staged tile are never written by the bulk copies: zero the ring once
-        const int ylo = my0 * a.sy - a.hy;
-        if (a.hz > 0 || ylo < 0 || ylo + a.BY > a.Yin) {
-            uint4* q = reinterpret_cast<uint4*>(smem + 1024);
-            const int n16 = (int)(a.nstage * a.stage_bytes / 16);
-            for (int i = threadIdx.x; i < n16; i += TC_THREADS) q[i] = make_uint4(0, 0, 0, 0);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    {
+        const int ncp = (a.out_mode == 1 ? 16 : (a.cout + 15) / 16 * 16);   // all n-slices (<= 256 channels)
+        for (int i = threadIdx.x; i < ncp; i += TC_THREADS) {
+            ep_c[i] = a.ep.scale[i];
+            ep_c[256 + i] = a.ep.shift[i];
+            ep_c[512 + i] = a.nchunk2 ? a.bias2[i] : 0.f;
+            ep_c[768 + i] = a.res_mode == 2 ? a.res_w[i] : 0.f;
+            ep_c[1024 + i] = a.res_mode == 2 ? a.res_b[i] : 0.f;
         }
+    }
+    if (a.line_mode && a.hz > 0) {
+        // z-halo rows at the volume border are never written when the z tile spans the whole volume:
+        // zero the ring once (with several z tiles the producer writes them from g_zero_line instead)
+        uint4* q = reinterpret_cast<uint4*>(smem + TC_HDR);
+        const int n16 = (int)(a.nstage * a.stage_bytes / 16);
+        for (int i = threadIdx.x; i < n16; i += TC_THREADS) q[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -244,181 +287,225 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     if (warp == 0 && a.line_mode) {
         // ===== bulk-copy producer: every lane issues whole z lines (2 KB contiguous in act8) =====
         int it = 0;
-        for (int s = 0; s < ntot; ++s) {
-            const bool seg2 = s >= nmain;
-            const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
-            const int x = seg2 ? mx : mx * a.sx + j + a.xoff;
-            if (x < 0 || x >= a.Xin || j >= njx) continue;
-            const int st = it % a.nstage;
-            mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
-            const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-            const vsseg_act8& src = seg2 ? a.in2 : a.in;
-            // staged lines i in [i0, i1): input y = ybase + i; rows z in [zlo, zhi)
-            const int sy = seg2 ? 1 : a.sy;
-            const int ybase = my0 * sy - a.hy;
-            int i0 = seg2 ? a.hy : 0, i1 = seg2 ? a.hy + a.YL : a.BY;
-            i0 = max(i0, -ybase);
-            i1 = min(i1, a.Yin - ybase);
-            const int zlo = max(mz0 - a.hz, 0), zhi = min(mz0 + a.LZ + a.hz, a.Zin);
-            const uint32_t row_bytes = (uint32_t)(zhi - zlo) * 16;
-            const int ncopy = max(i1 - i0, 0) * 4;
-            if (lane == 0) {
-                const uint32_t bb = seg2 ? a.b2_bytes : a.b_bytes;
-                mbar_expect_tx(full + st, (uint32_t)ncopy * row_bytes + bb);
-                const uint8_t* wsrc = seg2 ? a.w2 + ((size_t)ns * a.nchunk2 + c) * a.b2_bytes
-                                           : a.w + ((size_t)(sel * a.nchunk + c) * a.nj + j) * a.b_bytes;
-                bulk_load(base + a.b_off, wsrc, bb, full + st);
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            const TcTile T = decode_tile(a, tile);
+            for (int s = 0; s < ntot; ++s) {
+                const bool seg2 = s >= nmain;
+                const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
+                const int x = seg2 ? T.mx : T.mx * a.sx + j + a.xoff;
+                if (x < 0 || x >= a.Xin || j >= T.njx) continue;
+                const int st = it % a.nstage;
+                mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+                const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                const vsseg_act8& src = seg2 ? a.in2 : a.in;
+                // staged lines i in [i0, i1): input y = ybase + i (zero line when outside); rows z in [zlo, zhi)
+                const int sy = seg2 ? 1 : a.sy;
+                const int ybase = T.my0 * sy - a.hy;
+                const int i0 = seg2 ? a.hy : 0, i1 = seg2 ? a.hy + a.YL : a.BY;
+                const int zlo = max(T.mz0 - a.hz, 0), zhi = min(T.mz0 + a.LZ + a.hz, a.Zin);
+                const uint32_t row_bytes = (uint32_t)(zhi - zlo) * 16;
+                const int ncopy = (i1 - i0) * 4;
+                // with several z tiles the border halo rows must be rewritten as zeros
+                const bool zl = a.ntz > 1 && a.hz > 0 && T.mz0 - a.hz < 0, zh = a.ntz > 1 && a.hz > 0 && T.mz0 + a.LZ + a.hz > a.Zin;
+                if (lane == 0) {
+                    const uint32_t bb = seg2 ? a.b2_bytes : a.b_bytes;
+                    mbar_expect_tx(full + st, (uint32_t)ncopy * (row_bytes + (zl ? 16u : 0u) + (zh ? 16u : 0u)) + bb);
+                    const uint8_t* wsrc = seg2 ? a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes
+                                               : a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + j) * a.b_bytes;
+                    bulk_load(base + a.b_off, wsrc, bb, full + st);
+                }
+                const __nv_bfloat16* g0 = (const __nv_bfloat16*)src.hi + (int64_t)T.b * src.batch_stride;
+                for (int q = lane; q < ncopy; q += 32) {
+                    const int i = i0 + (q >> 2), plane = (q >> 1) & 1, cg = q & 1;
+                    const int y = ybase + i;
+                    const void* gp = (y >= 0 && y < a.Yin)
+                                         ? (const void*)(g0 + (int64_t)plane * src.lo_offset +
+                                                         ((((int64_t)(2 * c + cg) * a.Xin + x) * a.Yin + y) * a.Zin + zlo) * 8)
+                                         : (const void*)g_zero_line;
+                    const uint32_t line = base + (uint32_t)plane * a.a_plane + (uint32_t)cg * a.lbo_a + (uint32_t)(i * a.pitch) * 16;
+                    bulk_load(line + (uint32_t)(zlo - (T.mz0 - a.hz)) * 16, gp, row_bytes, full + st);
+                    if (zl) bulk_load(line, g_zero_line, 16, full + st);
+                    if (zh) bulk_load(line + (uint32_t)(a.pitch - 1) * 16, g_zero_line, 16, full + st);
+                }
+                __syncwarp();
+                ++it;
             }
-            const __nv_bfloat16* g0 = (const __nv_bfloat16*)src.hi + (int64_t)b * src.batch_stride;
-            for (int q = lane; q < ncopy; q += 32) {
-                const int i = i0 + (q >> 2), plane = (q >> 1) & 1, cg = q & 1;
-                const __nv_bfloat16* gp = g0 + (int64_t)plane * src.lo_offset +
-                                          ((((int64_t)(2 * c + cg) * a.Xin + x) * a.Yin + (ybase + i)) * a.Zin + zlo) * 8;
-                const uint32_t dst = base + (uint32_t)plane * a.a_plane + (uint32_t)cg * a.lbo_a +
-                                     (uint32_t)(i * a.pitch + (zlo - (mz0 - a.hz))) * 16;
-                bulk_load(dst, gp, row_bytes, full + st);
-            }
-            __syncwarp();
-            ++it;
         }
     } else if (warp == 0) {
         if (elect_one()) {
             // ===== TMA producer =====
             int it = 0;
-            for (int s = 0; s < ntot; ++s) {
-                const bool seg2 = s >= nmain;
-                const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
-                const int x = seg2 ? mx : mx * a.sx + j + a.xoff;
-                if (x < 0 || x >= a.Xin || j >= njx) continue;  // plane is padding: stage skipped on both sides
-                const int st = it % a.nstage;
-                mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
-                const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-                const CUtensorMap* map = seg2 ? &tmap2 : &tmap;
-                const int cgp = seg2 ? a.cg_plane2 : a.cg_plane;
-                const int cgi = b * (seg2 ? a.cg_batch2 : a.cg_batch) + c * 2;
-                if (!seg2) {
-                    mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + a.b_bytes);
-                    for (int i = 0; i < a.nbox; ++i) {
-                        const uint32_t dst = base + (uint32_t)a.boxes[i].dst16 * 16;
-                        const int zc = mz0 * a.sz + a.boxes[i].dz, yc = my0 * a.sy + a.boxes[i].dy;
-                        tma_load_5d(dst, map, full + st, 0, zc, yc, x, cgi);
-                        tma_load_5d(dst + a.a_plane, map, full + st, 0, zc, yc, x, cgi + cgp);
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const TcTile T = decode_tile(a, tile);
+                for (int s = 0; s < ntot; ++s) {
+                    const bool seg2 = s >= nmain;
+                    const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
+                    const int x = seg2 ? T.mx : T.mx * a.sx + j + a.xoff;
+                    if (x < 0 || x >= a.Xin || j >= T.njx) continue;  // plane is padding: stage skipped on both sides
+                    const int st = it % a.nstage;
+                    mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+                    const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                    const CUtensorMap* map = seg2 ? &tmap2 : &tmap;
+                    const int cgp = seg2 ? a.cg_plane2 : a.cg_plane;
+                    const int cgi = T.b * (seg2 ? a.cg_batch2 : a.cg_batch) + c * 2;
+                    if (!seg2) {
+                        mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + a.b_bytes);
+                        for (int i = 0; i < a.nbox; ++i) {
+                            const uint32_t dst = base + (uint32_t)a.boxes[i].dst16 * 16;
+                            const int zc = T.mz0 * a.sz + a.boxes[i].dz, yc = T.my0 * a.sy + a.boxes[i].dy;
+                            tma_box(a.map_wide, dst, map, full + st, zc, yc, x, cgi);
+                            tma_box(a.map_wide, dst + a.a_plane, map, full + st, zc, yc, x, cgi + cgp);
+                        }
+                        bulk_load(base + a.b_off, a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + j) * a.b_bytes, a.b_bytes,
+                                  full + st);
+                    } else {
+                        // shortcut source: same box shape, unshifted in z, 1x1x1 weights
+                        mbar_expect_tx(full + st, 2 * a.box_tx + a.b2_bytes);
+                        const int zc = T.mz0 + a.dz2, yc = T.my0 + a.dy2;
+                        tma_box(a.map_wide, base, map, full + st, zc, yc, x, cgi);
+                        tma_box(a.map_wide, base + a.a_plane, map, full + st, zc, yc, x, cgi + cgp);
+                        bulk_load(base + a.b_off, a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes, a.b2_bytes, full + st);
                     }
-                    bulk_load(base + a.b_off, a.w + ((size_t)(sel * a.nchunk + c) * a.nj + j) * a.b_bytes, a.b_bytes,
-                              full + st);
-                } else {
-                    // shortcut source: same box shape, first box only (dy, dz of box 0), 1x1x1 weights
-                    mbar_expect_tx(full + st, 2 * a.box_tx + a.b2_bytes);
-                    const int zc = mz0 + a.dz2, yc = my0 + a.dy2;
-                    tma_load_5d(base, map, full + st, 0, zc, yc, x, cgi);
-                    tma_load_5d(base + a.a_plane, map, full + st, 0, zc, yc, x, cgi + cgp);
-                    bulk_load(base + a.b_off, a.w2 + ((size_t)ns * a.nchunk2 + c) * a.b2_bytes, a.b2_bytes, full + st);
+                    ++it;
                 }
-                ++it;
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             // ===== MMA issuer (one elected lane; every MMA accumulates into TMEM zeroed by the epilogue warps) =====
-            mbar_wait(tmem_zero, 0);
-            tc_fence_after();
-            int it = 0;
-            for (int s = 0; s < ntot; ++s) {
-                const bool seg2 = s >= nmain;
-                const int j = seg2 ? 0 : s % a.nj;
-                const int x = seg2 ? mx : mx * a.sx + j + a.xoff;
-                if (x < 0 || x >= a.Xin || j >= njx) continue;
-                const int st = it % a.nstage;
-                mbar_wait(full + st, (it / a.nstage) & 1);
+            int it = 0, k = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+                const TcTile T = decode_tile(a, tile);
+                const int buf = k % a.nbuf;
+                mbar_wait(acc_empty + buf, (k / a.nbuf) & 1);   // drained and re-zeroed by the epilogue warps
                 tc_fence_after();
-                const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-                const uint64_t da = make_desc(base, a.lbo_a, 128);
-                if (!seg2) {
-                    const uint64_t db = make_desc(base + a.b_off, a.lbo_b, 128);
+                const uint32_t tacc = tmem_base + (uint32_t)buf * buf_cols;
+                for (int s = 0; s < ntot; ++s) {
+                    const bool seg2 = s >= nmain;
+                    const int j = seg2 ? 0 : s % a.nj;
+                    const int x = seg2 ? T.mx : T.mx * a.sx + j + a.xoff;
+                    if (x < 0 || x >= a.Xin || j >= T.njx) continue;
+                    const int st = it % a.nstage;
+                    mbar_wait(full + st, (it / a.nstage) & 1);
+                    tc_fence_after();
+                    const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                    const uint64_t da = make_desc(base, a.lbo_a, 128);
+                    if (!seg2) {
+                        const uint64_t db = make_desc(base + a.b_off, a.lbo_b, 128);
 #pragma unroll 4
-                    for (int i = 0; i < a.nop; ++i) {
-                        const TcOp op = a.ops[i];
-                        umma_bf16(tmem_base + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                        for (int i = 0; i < a.nop; ++i) {
+                            const TcOp op = a.ops[i];
+                            umma_bf16(tacc + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                        }
+                    } else {
+                        const uint64_t db = make_desc(base + a.b_off, a.lbo_b2, 128);
+                        for (int i = 0; i < a.nop2; ++i) {
+                            const TcOp op = a.ops2[i];
+                            umma_bf16(tacc + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                        }
                     }
-                } else {
-                    const uint64_t db = make_desc(base + a.b_off, a.lbo_b2, 128);
-                    for (int i = 0; i < a.nop2; ++i) {
-                        const TcOp op = a.ops2[i];
-                        umma_bf16(tmem_base + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
-                    }
+                    umma_commit(empty + st);
+                    ++it;
                 }
-                umma_commit(empty + st);
-                ++it;
+                umma_commit(acc_full + buf);
             }
-            umma_commit(acc_full);
         }
     } else {
         // ===== epilogue: 4 warps, TMEM lanes (warp % 4) * 32 .. +31, thread = one M-tile row =====
         const int lane_base = (warp & 3) * 32;
-        {   // zero this warp's lanes of every accumulator column, then release the MMA issuer
-            const uint32_t used = (uint32_t)(a.nacc * (a.nchunk2 ? 2 : 1) * a.n_cta);
-            for (uint32_t c = 0; c < used; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)lane_base << 16) + c);
+        const uint32_t tlane = tmem_base + ((uint32_t)lane_base << 16);
+        // zero this warp's lanes of every accumulator buffer, then release the MMA issuer
+        for (int bf = 0; bf < a.nbuf; ++bf) {
+            for (uint32_t c = 0; c < buf_cols; c += 16) tmem_st16_zero(tlane + (uint32_t)bf * buf_cols + c);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_zero);
+            if (lane == 0) mbar_arrive(acc_empty + bf);
         }
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
         const int r = lane_base + lane;
         const int ly = r / a.LZ, zz = r % a.LZ;
         const int Xo = a.out.X, Yo = a.out.Y, Zo = a.out.Z;
-        const int ox = mx * a.ux + px;
-        const int co0 = ns * a.n_cta;
-        const int nreal = min(a.n_cta, a.cout - co0);
         const uint32_t sc_col = (uint32_t)(a.nacc * a.n_cta);  // shortcut accumulators follow the main ones
         __nv_bfloat16* out_hi = (__nv_bfloat16*)a.out.hi;
-        for (int ai = 0; ai < a.nacc; ++ai) {
-            // rows of a partial (zero-padded) line group load their TMEM lane like everyone else
-            // (tcgen05.ld is warp-collective) but neither read the residual nor store
-            const bool valid = my0 + ly + (a.accs[ai].y_add / a.uy) < a.Ym;
-            const int oy = (my0 + ly) * a.uy + a.accs[ai].y_add;
-            const int oz = (mz0 + zz) * a.uz + a.accs[ai].z_add;
-            float rsrc = 0.f;
-            if (a.res_mode == 2 && valid) rsrc = a.rsrc.ptr[b * a.rsrc.sb + ox * a.rsrc.sx + oy * a.rsrc.sy + oz * a.rsrc.sz];
-            for (int c0 = 0; c0 < nreal; c0 += 16) {
-                uint32_t v[16], v2[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(ai * a.n_cta + c0);
-                tmem_ld16(taddr, v);
-                if (a.nchunk2) tmem_ld16(taddr + sc_col, v2);
-                tmem_ld_wait();
-                if (!valid) continue;
-#pragma unroll
-                for (int g8 = 0; g8 < 2; ++g8) {
-                    const int cc = co0 + c0 + g8 * 8;
-                    if (c0 + g8 * 8 >= nreal) break;
-                    float o[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float f = __uint_as_float(v[g8 * 8 + q]) * __ldg(a.ep.scale + cc + q) + __ldg(a.ep.shift + cc + q);
-                        o[q] = apply_act(f, a.ep.act, a.ep.slope);
+        int k = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+            const TcTile T = decode_tile(a, tile);
+            const int buf = k % a.nbuf;
+            const uint32_t tacc = tlane + (uint32_t)buf * buf_cols;
+            const int b = T.b, my0 = T.my0, mz0 = T.mz0;
+            const int ox = T.mx * a.ux + T.px;
+            const int co0 = T.ns * a.n_cta;
+            const int nreal = min(a.n_cta, a.cout - co0);
+            mbar_wait(acc_full + buf, (k / a.nbuf) & 1);
+            tc_fence_after();
+            for (int ai = 0; ai < a.nacc; ++ai) {
+                // rows of a partial (zero-padded) line group load their TMEM lane like everyone else
+                // (tcgen05.ld is warp-collective) but neither read the residual nor store
+                const bool valid = my0 + ly + (a.accs[ai].y_add / a.uy) < a.Ym;
+                const int oy = (my0 + ly) * a.uy + a.accs[ai].y_add;
+                const int oz = (mz0 + zz) * a.uz + a.accs[ai].z_add;
+                float rsrc = 0.f;
+                if (a.res_mode == 2 && valid) rsrc = a.rsrc.ptr[b * a.rsrc.sb + ox * a.rsrc.sx + oy * a.rsrc.sy + oz * a.rsrc.sz];
+                for (int c0 = 0; c0 < nreal; c0 += 16) {
+                    uint32_t v[16], v2[16];
+                    const uint32_t taddr = tacc + (uint32_t)(ai * a.n_cta + c0);
+                    tmem_ld16(taddr, v);
+                    if (a.nchunk2) tmem_ld16(taddr + sc_col, v2);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+                    if (a.out_mode == 1) {
+                        // planar fp32 output: attention map (sigmoid) or logits, optionally blended into the
+                        // sliding-window accumulator (MONAI sliding_window_inference step 6)
+                        const float sw = a.sw_weight ? __ldg(a.sw_weight + ((int64_t)ox * Yo + oy) * Zo + oz) : 0.f;
+                        for (int q = 0; q < a.cout; ++q) {
+                            float f = __uint_as_float(v[q]) * ep_c[q] + ep_c[256 + q];
+                            f = apply_act(f, a.ep.act, a.ep.slope);
+                            float* o = a.outf.ptr + b * a.outf.sb + q * a.outf.sc + ox * a.outf.sx + oy * a.outf.sy + oz * a.outf.sz;
+                            if (a.sw_weight) *o += sw * f;
+                            else *o = f;
+                        }
+                        continue;
                     }
-                    if (a.nchunk2) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) o[q] += __uint_as_float(v2[g8 * 8 + q]) + __ldg(a.bias2 + cc + q);
+                    for (int g8 = 0; g8 < 2; ++g8) {
+                        const int cc = co0 + c0 + g8 * 8;
+                        if (c0 + g8 * 8 >= nreal) break;
+                        float o[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float f = __uint_as_float(v[g8 * 8 + q]) * ep_c[cc + q] + ep_c[256 + cc + q];
+                            o[q] = apply_act(f, a.ep.act, a.ep.slope);
+                        }
+                        if (a.nchunk2) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) o[q] += __uint_as_float(v2[g8 * 8 + q]) + ep_c[512 + cc + q];
+                        }
+                        if (a.res_mode == 1) {
+                            const __nv_bfloat16* rp = (const __nv_bfloat16*)a.res.hi +
+                                                      act8_off(a.res.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
+                            float rr[8];
+                            unpack8(ldg128(rp), ldg128(rp + a.res.lo_offset), rr);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) o[q] += rr[q];
+                        } else if (a.res_mode == 2) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) o[q] += ep_c[768 + cc + q] * rsrc + ep_c[1024 + cc + q];
+                        }
+                        uint4 h, l;
+                        pack8(o, h, l);
+                        __nv_bfloat16* p = out_hi + act8_off(a.out.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
+                        *reinterpret_cast<uint4*>(p) = h;
+                        *reinterpret_cast<uint4*>(p + a.out.lo_offset) = l;
                     }
-                    if (a.res_mode == 1) {
-                        const __nv_bfloat16* rp = (const __nv_bfloat16*)a.res.hi +
-                                                  act8_off(a.res.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
-                        float rr[8];
-                        unpack8(ldg128(rp), ldg128(rp + a.res.lo_offset), rr);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) o[q] += rr[q];
-                    } else if (a.res_mode == 2) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) o[q] += __ldg(a.res_w + cc + q) * rsrc + __ldg(a.res_b + cc + q);
-                    }
-                    uint4 h, l;
-                    pack8(o, h, l);
-                    __nv_bfloat16* p = out_hi + act8_off(a.out.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
-                    *reinterpret_cast<uint4*>(p) = h;
-                    *reinterpret_cast<uint4*>(p + a.out.lo_offset) = l;
                 }
+            }
+            // re-zero the drained buffer for its next tile and hand it back to the MMA issuer
+            if (tile + a.nbuf * (int)gridDim.x < a.ntiles) {
+                for (uint32_t c = 0; c < buf_cols; c += 16) tmem_st16_zero(tacc + c);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + buf);
             }
         }
     }
@@ -436,6 +523,17 @@ struct TcPlan {
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;  // B200; also the answer on the GPU-less build box
+        cudaGetLastError();
+    }
+    return sms;
+}
 
 struct TcGeom {   // what gen_ops needs
     bool tr, strided, line;
@@ -573,7 +671,7 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     // flavour
     // line mode: M tile = one z line; the stage holds BY whole input lines (pitch = 128 + 2*hz rows),
     // every tap is an address offset (line, dz) into it.  Needs unit z stride.
-    const bool line = LY == 1 && g->sz == 1;
+    const bool line = LY == 1 && g->sz == 1 && KZ == 3;   // without a z halo one wide TMA box moves whole lines
     const int sy_in = tr ? 1 : g->sy;
     // choose YT = number of y line groups per CTA
     const int ygroups = (Ym + LY - 1) / LY;   // a partial last group is zero-filled by TMA and masked in the epilogue
@@ -612,21 +710,23 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
         }
         const size_t stage = 2 * a_plane + round_up((int)b_bytes, 128);
         if (stage / 16 >= 16000) break;
-        const long budget = 227L * 1024 - 1024, half = 113L * 1024 - 1024;
+        const long budget = 227L * 1024 - TC_HDR;
         int nst = (int)(budget / (long)stage);
         if (nst < 2) break;
-        // cost model: tiles per SM x (stages x max(MMA time, smem fill time at ~32 B/cycle/SM) + a fixed
-        // prologue/epilogue cost that a second co-resident CTA mostly hides)
+        // cost model (persistent CTAs, one per SM): tiles per SM x tile time; tile time = main loop
+        // (stages x max(MMA cycles, smem fill at ~32 B/cycle/SM)) and epilogue, overlapped when the
+        // accumulators can be double-buffered in TMEM, serialised (plus pipeline refill) when not
         const long tiles = total_tiles_1 * (ygroups / YT);
-        const bool two = 2 * (long)stage <= half && YT * acc_mult * n_cta <= 256;
+        const bool dbuf = YT * acc_mult * n_cta <= 256;
         const double fill_cyc = (double)stage / 32.0;
         const double stage_cyc = mma_cyc > fill_cyc ? mma_cyc : fill_cyc;
-        const double tile_cyc = stages_total * stage_cyc + (two ? 1500.0 : 5000.0);
-        const double cost = (double)((tiles + 147) / 148) * tile_cyc;
+        const double main_cyc = stages_total * stage_cyc;
+        const double epi_cyc = 300.0 + YT * nphase * (n_cta / 16) * 260.0;
+        const double tile_cyc = dbuf ? (main_cyc > epi_cyc ? main_cyc : epi_cyc) + 200.0 : main_cyc + epi_cyc + 1500.0;
+        const double cost = (double)((tiles + 147) / 148) * tile_cyc + 4000.0;
         if (cost < best_cost) {
             best_cost = cost; best = YT; best_stage = stage;
-            best_nstage = two ? (int)(half / (long)stage) : nst;
-            if (best_nstage > 4) best_nstage = 4;
+            best_nstage = nst > 6 ? 6 : nst;
         }
     }
     if (!best) return false;
@@ -671,6 +771,7 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     }
     a.ux = tr ? 2 : 1; a.uy = tr ? 2 : 1; a.uz = tr ? g->sz : 1;
     a.line_mode = line ? 1 : 0;
+    a.map_wide = (!line && !(strided && g->sz == 2)) ? 1 : 0;
     a.BY = BY; a.pitch = BZ; a.hy = tr ? 0 : hy; a.hz = hz; a.Yin = in->Y; a.Zin = in->Z;
     a.in = *in;
     if (src2) a.in2 = *src2;
@@ -706,14 +807,18 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
         a.dy2 = -hy;
         a.dz2 = 0;
     }
-    const int cols = nacc * (src2 ? 2 : 1) * n_cta;
+    a.ntiles = (int)((long)in->B * a.ntx * a.nty * a.ntz * a.nsel);
+    const int sms = sm_count();
+    const int cols1 = nacc * (src2 ? 2 : 1) * n_cta;
+    a.nbuf = (cols1 <= 256 && a.ntiles > sms) ? 2 : 1;   // double-buffered accumulators when a CTA walks several tiles
+    const int cols = cols1 * a.nbuf;
     a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     P->box[0] = 8; P->box[1] = (cuuint32_t)(BZ * (strided ? g->sz : 1)); P->box[2] = (cuuint32_t)(BY * (strided ? g->sy : 1));
     P->box[3] = 1; P->box[4] = 2;
     P->estr[0] = 1; P->estr[1] = (cuuint32_t)(strided ? g->sz : 1); P->estr[2] = (cuuint32_t)(strided ? g->sy : 1);
     P->estr[3] = 1; P->estr[4] = 1;
-    P->smem = 1024 + (size_t)a.nstage * a.stage_bytes;
-    P->grid = (unsigned)((long)in->B * a.ntx * a.nty * a.ntz * a.nsel);
+    P->smem = TC_HDR + (size_t)a.nstage * a.stage_bytes;
+    P->grid = (unsigned)(a.ntiles < sms ? a.ntiles : sms);   // persistent: one CTA per SM
     return true;
 }
 
@@ -739,12 +844,36 @@ static int encode_map(CUtensorMap* tmap, const vsseg_act8* t, int cg_plane, int 
     const cuuint64_t gdim[5] = {8, (cuuint64_t)t->Z, (cuuint64_t)t->Y, (cuuint64_t)t->X,
                                 (cuuint64_t)(cg_plane + (t->B - 1) * cg_batch + t->C / 8)};
     const cuuint64_t gstr[4] = {16, (cuuint64_t)t->Z * 16, (cuuint64_t)t->Y * t->Z * 16, (cuuint64_t)cgs * 2};
-    CUresult cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t->hi, gdim, gstr, P.box, P.estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult cr;
+    if (P.a.map_wide) {
+        // (z, 8 channels) merged into one dimension of 8-byte elements: 2 per voxel, a box row = a z line
+        const cuuint64_t gdim4[4] = {(cuuint64_t)t->Z * 2, gdim[2], gdim[3], gdim[4]};
+        const cuuint32_t box4[4] = {P.box[1] * 2, P.box[2], 1, 2};
+        const cuuint32_t estr4[4] = {1, P.estr[2], 1, 1};
+        cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, t->hi, gdim4, gstr + 1, box4, estr4,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t->hi, gdim, gstr, P.box, P.estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (cr != CUDA_SUCCESS) {
         set_error("conv3d_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         return (int)cr;
+    }
+    return 0;
+}
+
+static int set_smem_attr() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("conv3d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set = true;
     }
     return 0;
 }
@@ -781,6 +910,31 @@ int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, c
         if ((long)P.grid >= 120 || tiles * s >= 120) break;
     }
     return best;
+}
+
+int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
+                           const vsseg_epilogue* ep, const float* sw_weight, void* stream) {
+    VSSEG_REQUIRE(in && out && out->ptr && out->C >= 1 && out->C <= 16, "conv3d_tc_f32out: Cout must be 1..16");
+    // the plan only needs the output extents: describe the planar output as a 16-channel act8 tensor
+    vsseg_act8 o16{};
+    o16.hi = out->ptr; o16.B = out->B; o16.C = 16; o16.X = out->X; o16.Y = out->Y; o16.Z = out->Z;
+    static TcPlan P;
+    VSSEG_REQUIRE(g && !g->transposed && g->sx == 1 && g->sy == 1 && g->sz == 1 && make_plan(in, &o16, g, 1, nullptr, &P),
+                  "conv3d_tc_f32out: unsupported shape (stride-1 convs covered by vsseg_conv3d_tc_supported)");
+    VSSEG_REQUIRE(w_packed && ep && ep->scale && ep->shift, "conv3d_tc_f32out: NULL weights/epilogue");
+    TcArgs& a = P.a;
+    a.ep = *ep;
+    a.w = (const uint8_t*)w_packed;
+    a.out_mode = 1;
+    a.outf = *out;
+    a.cout = out->C;
+    a.sw_weight = sw_weight;
+    CUtensorMap tmap;
+    if (a.line_mode) memset(&tmap, 0, sizeof(tmap));
+    else if (int e = encode_map(&tmap, in, a.cg_plane, a.cg_batch, P)) return e;
+    if (int e = set_smem_attr()) return e;
+    conv_tc_kernel<<<P.grid, TC_THREADS, P.smem, (cudaStream_t)stream>>>(tmap, tmap, a);
+    return check_launch("conv3d_tc_f32out");
 }
 
 int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int32_t n_split,
@@ -842,15 +996,7 @@ int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_con
             tmap2 = tmap;
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) {
-            set_error("conv3d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr_set = true;
-    }
+    if (int e = set_smem_attr()) return e;
     conv_tc_kernel<<<P.grid, TC_THREADS, P.smem, (cudaStream_t)stream>>>(tmap, tmap2, a);
     return check_launch("conv3d_tc");
 }

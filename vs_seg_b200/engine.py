@@ -189,8 +189,9 @@ class UNetEvalPlan:
         """src/dst: Act8 views.  One fused Convolution block (+ optional residual).
         shortcut = (prefix of the 1x1x1 residual conv, its Act8 source): fused as a second accumulator
         on the tensor-core path; returns False if it could not be fused (caller adds it separately)."""
-        cout = dst.C
-        cpad = _round_up(cout, 16)
+        wshape = self.sd[p + "conv.weight"].shape
+        cout = wshape[1] if transposed else wshape[0]  # dst may carry zero-padded extra channels (cout < dst.C)
+        cpad = _round_up(dst.C, 16)
         scale, shift, slope, code = fold_epilogue(self.sd, p, cout, cpad, norm, act)
         scale, shift = self._dev(scale), self._dev(shift)
         ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
@@ -210,7 +211,8 @@ class UNetEvalPlan:
                 sc_p = None
                 ns = self.lib.vsseg_conv3d_tc_suggest_split(C.byref(src), C.byref(dst), C.byref(g), None)
             if ns > 0:
-                w = self._dev(pack_conv_weight_tc(self.sd[p + "conv.weight"], transposed, ns))
+                w = self._dev(pack_conv_weight_tc(self._pad_cout(self.sd[p + "conv.weight"], transposed, dst.C),
+                                                  transposed, ns))
                 sc_tail = (None, None, None)
                 if fused:
                     q = shortcut[0]
@@ -228,6 +230,43 @@ class UNetEvalPlan:
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
         return False
 
+    @staticmethod
+    def _pad_cout(w, transposed, c):
+        """Zero-pad the output channels of a conv weight to c (extra channels of the act8 buffer stay 0)."""
+        d = 1 if transposed else 0
+        if w.shape[d] == c:
+            return w
+        pad = [0, 0] * (w.dim() - 1 - d) + [0, c - w.shape[d]]
+        return torch.nn.functional.pad(w, pad)
+
+    def _add_smallcout(self, name, src, out_view, k, w, bias, act_code, slope, sw_weight=None, nb_extra=0):
+        """Conv with 1-2 output channels -> planar fp32: tensor-core path when the shape is covered
+        (weights zero-padded to Cin = src.C, Cout = 16), else the CUDA-core kernel."""
+        g = self._geom(k)
+        cout = w.shape[0]
+        fl, nb = _conv_cost(src, src, k, False, src.C, cout)  # stride 1: output extents = input extents
+        nb += nb_extra
+        if w.shape[1] != src.C:  # hidden buffer padded to a multiple of 16 channels
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, src.C - w.shape[1]))
+        self._keep += [src, out_view, g]
+        if self.use_tc and src.C % 16 == 0:
+            o16 = _lib.Act8(src.hi, 0, 0, src.B, 16, src.X, src.Y, src.Z)  # extents only (plan check)
+            if self.lib.vsseg_conv3d_tc_supported(C.byref(src), C.byref(o16), C.byref(g), 1, None):
+                wp = self._dev(pack_conv_weight_tc(self._pad_cout(w, False, 16), False, 1))
+                scale = self._dev(torch.ones(16))
+                shift = self._dev(torch.nn.functional.pad(bias.float(), (0, 16 - cout)))
+                ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, act_code)
+                self._keep.append(ep)
+                self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc_f32out,
+                                        (C.byref(src), C.byref(out_view), C.byref(g), wp.data_ptr(), C.byref(ep),
+                                         sw_weight), fl, nb, kind="tcgen05"))
+                return
+        wg = self._dev(pack_conv_weight(w, False))
+        b = self._dev(bias.float())
+        self.steps.append(_Step(name, self.lib.vsseg_conv3d_smallcout,
+                                (C.byref(src), C.byref(out_view), C.byref(g), wg.data_ptr(), b.data_ptr(), act_code,
+                                 slope, sw_weight), fl, nb))
+
     def _add_shortcut(self, name, p, src, dst):
         """1x1x1 shortcut conv of a ResidualUnit (convolutions.py:241-250) -> addend buffer."""
         cout = dst.C
@@ -243,23 +282,19 @@ class UNetEvalPlan:
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
 
     def _add_att(self, name, p, buf, hid, k):
-        """AttentionBlock1+2 on act8 buffer `buf` (all channels), in place."""
+        """AttentionBlock1+2 on act8 buffer `buf` (all channels), in place.  The hidden tensor uses a
+        multiple of 16 channels (zero weights for the padding) so both convs run on tensor cores."""
         cin = buf.C
-        src, h = buf.view(), hid.view(0, cin // 2)
+        src, h = buf.view(), hid.view(0, _round_up(cin // 2, 16))
         self._add_conv(name + ".conv1", p + "0.conv1.", src, h, k, norm=False, act="relu")
         att = torch.empty((self.B, 1, buf.X, buf.Y, buf.Z), dtype=torch.float32, device=self.device)
         self.att_maps.append(att)
         av = f32view(att)
-        w2 = self._dev(pack_conv_weight(self.sd[p + "0.conv2.conv.weight"], False))  # [taps][C/2][1]
-        b2 = self._dev(self.sd[p + "0.conv2.conv.bias"].float())
-        g = self._geom(k)
-        fl, nb = _conv_cost(h, av, k, False, h.C, 1)
-        self.steps.append(_Step(name + ".conv2", self.lib.vsseg_conv3d_smallcout,
-                                (C.byref(h), C.byref(av), C.byref(g), w2.data_ptr(), b2.data_ptr(), 1, 0.0, None),
-                                fl, nb))
+        self._add_smallcout(name + ".conv2", h, av, k, self.sd[p + "0.conv2.conv.weight"],
+                            self.sd[p + "0.conv2.conv.bias"], 1, 0.0)
         self.steps.append(_Step(name + ".gate", self.lib.vsseg_att_gate, (C.byref(src), C.byref(av), C.byref(src)),
                                 2 * _nvox(src) * cin, 4 * _nvox(src) * (2 * cin + 1)))
-        self._keep += [src, h, av, g]
+        self._keep += [src, h, av]
 
     def _add_ru(self, name, p, src, h_buf, r_buf, dst, k, subunits):
         """ResidualUnit with `subunits` Convolution blocks and a 1x1x1 shortcut; src/dst act8 views.
@@ -293,7 +328,7 @@ class UNetEvalPlan:
         bot_h = self._buf(ch[-1], dims[-1])
         bot_r = self._buf(ch[-1], dims[-1])
         bot_o = self._buf(ch[-1], dims[-1])
-        bot_hid = self._buf(_round_up(ch[-2] // 2, 8), dims[-1])
+        bot_hid = self._buf(_round_up(ch[-2] // 2, 16), dims[-1])
         self.buffers = dict(cat=cat, h=hb, r=rb, down=dn, bot_h=bot_h, bot_r=bot_r, bot_o=bot_o)
 
         prefixes = []
@@ -351,19 +386,14 @@ class UNetEvalPlan:
             else:
                 # top unit: conv_only + shortcut, both linear -> one conv (shortcut folded into the
                 # centre tap), written to planar fp32 or blended into the sliding-window accumulator.
-                w = pack_conv_weight(self.sd[pr + "conv.unit0.conv.weight"], False).clone()
-                centre = (k[0] // 2 * k[1] + k[1] // 2) * k[2] + k[2] // 2
-                w[centre] += self.sd[pr + "residual.weight"].reshape(self.out_channels, -1).t().float()
-                w = self._dev(w)
-                bias = self._dev((self.sd[pr + "conv.unit0.conv.bias"] + self.sd[pr + "residual.bias"]).float())
-                g = self._geom(k)
+                w = self.sd[pr + "conv.unit0.conv.weight"].float().clone()
+                w[:, :, k[0] // 2, k[1] // 2, k[2] // 2] += self.sd[pr + "residual.weight"].reshape(
+                    self.out_channels, -1).float()
+                bias = self.sd[pr + "conv.unit0.conv.bias"] + self.sd[pr + "residual.bias"]
                 src = cat[0].view()
-                self._keep += [g, src]
-                fl, nb = _conv_cost(src, src, k, False, src.C, self.out_channels)
-                nb += 4 * _nvox(src) * (self.out_channels * (2 - src.C) + 1)  # out RMW + weight map, not Cin out
-                self.steps.append(_Step("dec0.logits", self.lib.vsseg_conv3d_smallcout,
-                                        (C.byref(src), C.byref(self.dst), C.byref(g), w.data_ptr(), bias.data_ptr(),
-                                         0, 1.0, self.sw_weight), fl, nb))
+                # bytes: out read-modify-write + weight map instead of a plain store
+                self._add_smallcout("dec0.logits", src, self.dst, k, w, bias, 0, 1.0, self.sw_weight,
+                                    nb_extra=4 * _nvox(src) * (self.out_channels + 1))
         del self.sd
 
     # -- execution ----------------------------------------------------------------------
