@@ -119,7 +119,7 @@ int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const
                               int32_t n_split, const vsseg_act8* shortcut_src);
 int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
                                   const vsseg_act8* shortcut_src);
-/* Tensor-core conv with 1..16 output channels written as planar fp32 (attention conv2 + Sigmoid,
+/* Tensor-core conv with 1 or 2 output channels written as planar fp32 (attention conv2 + Sigmoid,
  * reference attentionblock.py:21-30; the top ResidualUnit's conv_only unit with its 1x1x1 shortcut
  * folded into the centre tap, unet2d5_spvPA.py:186-190).  Same contract as vsseg_conv3d_smallcout:
  * with sw_weight the result is blended into `out` (out += sw_weight[v] * y, MONAI

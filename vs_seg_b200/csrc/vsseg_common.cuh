@@ -48,11 +48,13 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& h, uint4& l) {
     uint32_t hh[4], ll[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        uint32_t h0, l0, h1, l1;
-        split1(v[2 * i], h0, l0);
-        split1(v[2 * i + 1], h1, l1);
-        hh[i] = h0 | (h1 << 16);
-        ll[i] = l0 | (l1 << 16);
+        // two values per cvt: hi pair, residuals against the rounded values, lo pair
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        hh[i] = *reinterpret_cast<const uint32_t*>(&hp);
+        const float r0 = v[2 * i] - __uint_as_float(hh[i] << 16);
+        const float r1 = v[2 * i + 1] - __uint_as_float(hh[i] & 0xffff0000u);
+        const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
+        ll[i] = *reinterpret_cast<const uint32_t*>(&lp);
     }
     h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
     l = make_uint4(ll[0], ll[1], ll[2], ll[3]);

@@ -19,6 +19,7 @@
 // nothing is gathered by threads.  Epilogue warps: tcgen05.ld -> BN scale/shift -> PReLU/ReLU ->
 // (+ residual / + shortcut accumulator) -> split-bf16 -> global (act8).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "vsseg_common.cuh"
 
@@ -154,7 +155,7 @@ struct TcBox {       // one TMA box of a stage (issued for the hi and the lo pla
 struct TcAcc {       // where an accumulator lands in the output
     int16_t y_add;   // output y of M-tile line 0, relative to the tile's output y base
     int8_t z_add;    // output z phase
-    int8_t pad;
+    int8_t yl;       // M-grid line offset of the accumulator's line group (for the partial-group mask)
 };
 
 constexpr int TC_MAX_OPS = 144;
@@ -181,6 +182,7 @@ struct TcArgs {
     uint32_t lbo_a, lbo_b, lbo_b2, idesc, tmem_cols;
     // tile decomposition of the M grid
     int ntz, nty, ntx, nsel, npx, nsplit, ntiles, nbuf;
+    int XT, npl;             // x rows per tile; stages per chunk (x planes XT+2 when XT > 1, else x taps nj)
     int LZ, LY, YL, Ym;      // M-tile shape, y lines of the M grid per CTA tile, y extent of the M grid
     int n_cta;               // output channels per CTA (multiple of 16), n_real: channels to store
     int cout;                // real Cout (multiple of 8)
@@ -204,7 +206,8 @@ struct TcArgs {
 };
 
 constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
-constexpr int TC_THREADS = 192;  // warp 0: producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each draining every other accumulator
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0: producer, warp 1: MMA issuer + TMEM owner, rest: epilogue
 
 __device__ uint4 g_zero_line[136];  // source of padding lines / halo rows for the bulk-copy producer (zero-initialised)
 
@@ -216,11 +219,11 @@ __device__ __forceinline__ TcTile decode_tile(const TcArgs& a, int t) {
     T.sel = t % a.nsel; t /= a.nsel;
     T.tz = t % a.ntz; t /= a.ntz;
     T.ty = t % a.nty; t /= a.nty;
-    T.mx = t % a.ntx; t /= a.ntx;
+    T.mx = (t % a.ntx) * a.XT; t /= a.ntx;   // first x row of the tile
     T.b = t;
     T.px = T.sel / a.nsplit; T.ns = T.sel % a.nsplit;
     T.my0 = T.ty * a.YL; T.mz0 = T.tz * a.LZ;
-    T.njx = (a.npx == 2 && T.px == 0) ? 1 : a.nj;  // transposed conv, even x phase: only the centre x tap
+    T.njx = (a.npx == 2 && T.px == 0) ? 1 : a.npl;  // transposed conv, even x phase: only the centre x tap
     return T;
 }
 
@@ -242,8 +245,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const uint32_t ring = smem_u32(smem) + TC_HDR;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nmain = a.nchunk * a.nj, ntot = nmain + a.nchunk2;
-    const uint32_t buf_cols = (uint32_t)(a.nacc * (a.nchunk2 ? 2 : 1) * a.n_cta);
+    const int nmain = a.nchunk * a.npl, ntot = nmain + a.nchunk2 * a.XT;
+    const uint32_t row_cols = (uint32_t)(a.nacc * a.n_cta);
+    const uint32_t buf_cols = (uint32_t)a.XT * row_cols * (a.nchunk2 ? 2 : 1);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.nstage; ++i) {
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(acc_full + i, 1);
-            mbar_init(acc_empty + i, 4);
+            mbar_init(acc_empty + i, TC_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -291,8 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             const TcTile T = decode_tile(a, tile);
             for (int s = 0; s < ntot; ++s) {
                 const bool seg2 = s >= nmain;
-                const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
-                const int x = seg2 ? T.mx : T.mx * a.sx + j + a.xoff;
+                const int c = seg2 ? (s - nmain) / a.XT : s / a.npl, j = seg2 ? 0 : s % a.npl;
+                const int x = seg2 ? T.mx + (s - nmain) % a.XT : T.mx * a.sx + j + a.xoff;
                 if (x < 0 || x >= a.Xin || j >= T.njx) continue;
                 const int st = it % a.nstage;
                 mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
@@ -308,10 +312,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 // with several z tiles the border halo rows must be rewritten as zeros
                 const bool zl = a.ntz > 1 && a.hz > 0 && T.mz0 - a.hz < 0, zh = a.ntz > 1 && a.hz > 0 && T.mz0 + a.LZ + a.hz > a.Zin;
                 if (lane == 0) {
-                    const uint32_t bb = seg2 ? a.b2_bytes : a.b_bytes;
+                    // XT > 1: the plane feeds all x taps, so the stage carries the weights of every tap
+                    const uint32_t bb = seg2 ? a.b2_bytes : (a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes);
                     mbar_expect_tx(full + st, (uint32_t)ncopy * (row_bytes + (zl ? 16u : 0u) + (zh ? 16u : 0u)) + bb);
                     const uint8_t* wsrc = seg2 ? a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes
-                                               : a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + j) * a.b_bytes;
+                                               : a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + (a.XT > 1 ? 0 : j)) * a.b_bytes;
                     bulk_load(base + a.b_off, wsrc, bb, full + st);
                 }
                 const __nv_bfloat16* g0 = (const __nv_bfloat16*)src.hi + (int64_t)T.b * src.batch_stride;
@@ -339,8 +344,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 const TcTile T = decode_tile(a, tile);
                 for (int s = 0; s < ntot; ++s) {
                     const bool seg2 = s >= nmain;
-                    const int c = seg2 ? s - nmain : s / a.nj, j = seg2 ? 0 : s % a.nj;
-                    const int x = seg2 ? T.mx : T.mx * a.sx + j + a.xoff;
+                    const int c = seg2 ? (s - nmain) / a.XT : s / a.npl, j = seg2 ? 0 : s % a.npl;
+                    const int x = seg2 ? T.mx + (s - nmain) % a.XT : T.mx * a.sx + j + a.xoff;
                     if (x < 0 || x >= a.Xin || j >= T.njx) continue;  // plane is padding: stage skipped on both sides
                     const int st = it % a.nstage;
                     mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
@@ -349,14 +354,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     const int cgp = seg2 ? a.cg_plane2 : a.cg_plane;
                     const int cgi = T.b * (seg2 ? a.cg_batch2 : a.cg_batch) + c * 2;
                     if (!seg2) {
-                        mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + a.b_bytes);
+                        const uint32_t bb = a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes;
+                        mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + bb);
                         for (int i = 0; i < a.nbox; ++i) {
                             const uint32_t dst = base + (uint32_t)a.boxes[i].dst16 * 16;
                             const int zc = T.mz0 * a.sz + a.boxes[i].dz, yc = T.my0 * a.sy + a.boxes[i].dy;
                             tma_box(a.map_wide, dst, map, full + st, zc, yc, x, cgi);
                             tma_box(a.map_wide, dst + a.a_plane, map, full + st, zc, yc, x, cgi + cgp);
                         }
-                        bulk_load(base + a.b_off, a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + j) * a.b_bytes, a.b_bytes,
+                        bulk_load(base + a.b_off, a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + (a.XT > 1 ? 0 : j)) * a.b_bytes, bb,
                                   full + st);
                     } else {
                         // shortcut source: same box shape, unshifted in z, 1x1x1 weights
@@ -382,8 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 const uint32_t tacc = tmem_base + (uint32_t)buf * buf_cols;
                 for (int s = 0; s < ntot; ++s) {
                     const bool seg2 = s >= nmain;
-                    const int j = seg2 ? 0 : s % a.nj;
-                    const int x = seg2 ? T.mx : T.mx * a.sx + j + a.xoff;
+                    const int j = seg2 ? 0 : s % a.npl;
+                    const int x = seg2 ? T.mx + (s - nmain) % a.XT : T.mx * a.sx + j + a.xoff;
                     if (x < 0 || x >= a.Xin || j >= T.njx) continue;
                     const int st = it % a.nstage;
                     mbar_wait(full + st, (it / a.nstage) & 1);
@@ -392,16 +398,32 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     const uint64_t da = make_desc(base, a.lbo_a, 128);
                     if (!seg2) {
                         const uint64_t db = make_desc(base + a.b_off, a.lbo_b, 128);
+                        if (a.XT == 1) {
 #pragma unroll 4
-                        for (int i = 0; i < a.nop; ++i) {
-                            const TcOp op = a.ops[i];
-                            umma_bf16(tacc + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                            for (int i = 0; i < a.nop; ++i) {
+                                const TcOp op = a.ops[i];
+                                umma_bf16(tacc + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                            }
+                        } else {
+                            // plane j of the haloed tile feeds output row r = j - dx through x tap dx
+                            for (int dx = 0; dx < a.nj; ++dx) {
+                                const int r = j - dx;
+                                if (r < 0 || r >= a.XT) continue;
+                                const uint32_t tr = tacc + (uint32_t)r * row_cols;
+                                const uint64_t dbx = db + (uint64_t)(dx * (a.b_bytes >> 4));
+#pragma unroll 4
+                                for (int i = 0; i < a.nop; ++i) {
+                                    const TcOp op = a.ops[i];
+                                    umma_bf16(tr + op.col, da + op.a16, dbx + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                                }
+                            }
                         }
                     } else {
                         const uint64_t db = make_desc(base + a.b_off, a.lbo_b2, 128);
+                        const uint32_t tr = tacc + (uint32_t)a.XT * row_cols + (uint32_t)((s - nmain) % a.XT) * row_cols;
                         for (int i = 0; i < a.nop2; ++i) {
                             const TcOp op = a.ops2[i];
-                            umma_bf16(tacc + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                            umma_bf16(tr + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
                         }
                     }
                     umma_commit(empty + st);
@@ -411,12 +433,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             }
         }
     } else {
-        // ===== epilogue: 4 warps, TMEM lanes (warp % 4) * 32 .. +31, thread = one M-tile row =====
+        // ===== epilogue: TC_EPI_WARPS warps, TMEM lanes (warp % 4) * 32 .. +31, thread = one M-tile row;
+        // the warps sharing a lane quadrant take alternate accumulators =====
         const int lane_base = (warp & 3) * 32;
+        const int esub = (warp - 2) >> 2, nsub = TC_EPI_WARPS / 4;
         const uint32_t tlane = tmem_base + ((uint32_t)lane_base << 16);
         // zero this warp's lanes of every accumulator buffer, then release the MMA issuer
         for (int bf = 0; bf < a.nbuf; ++bf) {
-            for (uint32_t c = 0; c < buf_cols; c += 16) tmem_st16_zero(tlane + (uint32_t)bf * buf_cols + c);
+            for (int ra = esub; ra < a.XT * a.nacc; ra += nsub)      // the accumulators this warp will drain
+                for (int c = 0; c < a.n_cta; c += 16) {
+                    tmem_st16_zero(tlane + (uint32_t)bf * buf_cols + (uint32_t)(ra * a.n_cta + c));
+                    if (a.nchunk2) tmem_st16_zero(tlane + (uint32_t)bf * buf_cols + (uint32_t)a.XT * row_cols + (uint32_t)(ra * a.n_cta + c));
+                }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -425,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const int r = lane_base + lane;
         const int ly = r / a.LZ, zz = r % a.LZ;
         const int Xo = a.out.X, Yo = a.out.Y, Zo = a.out.Z;
-        const uint32_t sc_col = (uint32_t)(a.nacc * a.n_cta);  // shortcut accumulators follow the main ones
+        const uint32_t sc_col = (uint32_t)a.XT * row_cols;  // shortcut accumulators follow the main ones
         __nv_bfloat16* out_hi = (__nv_bfloat16*)a.out.hi;
         int k = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
@@ -433,22 +461,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             const int buf = k % a.nbuf;
             const uint32_t tacc = tlane + (uint32_t)buf * buf_cols;
             const int b = T.b, my0 = T.my0, mz0 = T.mz0;
-            const int ox = T.mx * a.ux + T.px;
             const int co0 = T.ns * a.n_cta;
             const int nreal = min(a.n_cta, a.cout - co0);
             mbar_wait(acc_full + buf, (k / a.nbuf) & 1);
             tc_fence_after();
-            for (int ai = 0; ai < a.nacc; ++ai) {
+            for (int ra = esub; ra < a.XT * a.nacc; ra += nsub) {
+                const int xr = ra / a.nacc, ai = ra - xr * a.nacc;
+                const int ox = (T.mx + xr) * a.ux + T.px;
                 // rows of a partial (zero-padded) line group load their TMEM lane like everyone else
                 // (tcgen05.ld is warp-collective) but neither read the residual nor store
-                const bool valid = my0 + ly + (a.accs[ai].y_add / a.uy) < a.Ym;
+                const bool valid = my0 + ly + a.accs[ai].yl < a.Ym;
                 const int oy = (my0 + ly) * a.uy + a.accs[ai].y_add;
                 const int oz = (mz0 + zz) * a.uz + a.accs[ai].z_add;
                 float rsrc = 0.f;
                 if (a.res_mode == 2 && valid) rsrc = a.rsrc.ptr[b * a.rsrc.sb + ox * a.rsrc.sx + oy * a.rsrc.sy + oz * a.rsrc.sz];
                 for (int c0 = 0; c0 < nreal; c0 += 16) {
                     uint32_t v[16], v2[16];
-                    const uint32_t taddr = tacc + (uint32_t)(ai * a.n_cta + c0);
+                    const uint32_t taddr = tacc + (uint32_t)(ra * a.n_cta + c0);
                     tmem_ld16(taddr, v);
                     if (a.nchunk2) tmem_ld16(taddr + sc_col, v2);
                     tmem_ld_wait();
@@ -457,7 +486,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                         // planar fp32 output: attention map (sigmoid) or logits, optionally blended into the
                         // sliding-window accumulator (MONAI sliding_window_inference step 6)
                         const float sw = a.sw_weight ? __ldg(a.sw_weight + ((int64_t)ox * Yo + oy) * Zo + oz) : 0.f;
-                        for (int q = 0; q < a.cout; ++q) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {   // Cout <= 2 on this path (static indices keep v[] in registers)
+                            if (q >= a.cout) break;
                             float f = __uint_as_float(v[q]) * ep_c[q] + ep_c[256 + q];
                             f = apply_act(f, a.ep.act, a.ep.slope);
                             float* o = a.outf.ptr + b * a.outf.sb + q * a.outf.sc + ox * a.outf.sx + oy * a.outf.sy + oz * a.outf.sz;
@@ -501,7 +532,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             }
             // re-zero the drained buffer for its next tile and hand it back to the MMA issuer
             if (tile + a.nbuf * (int)gridDim.x < a.ntiles) {
-                for (uint32_t c = 0; c < buf_cols; c += 16) tmem_st16_zero(tacc + c);
+                for (int ra = esub; ra < a.XT * a.nacc; ra += nsub)  // only the accumulators this warp drained
+                    for (int c = 0; c < a.n_cta; c += 16) {
+                        tmem_st16_zero(tacc + (uint32_t)(ra * a.n_cta + c));
+                        if (a.nchunk2) tmem_st16_zero(tacc + sc_col + (uint32_t)(ra * a.n_cta + c));
+                    }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -555,6 +590,7 @@ static bool gen_ops(const TcGeom& G, int YT, TcOp* ops, int* nop_out, TcAcc* acc
         for (int y = 0; y < YT; ++y) {
             accs[nacc].y_add = (int16_t)(y * G.LY);
             accs[nacc].z_add = 0;
+            accs[nacc].yl = (int8_t)(y * G.LY);
             for (int dy = 0; dy < G.KY; ++dy)
                 for (int dz = 0; dz < G.KZ; ++dz) {
                     uint32_t aoff;
@@ -574,6 +610,7 @@ static bool gen_ops(const TcGeom& G, int YT, TcOp* ops, int* nop_out, TcAcc* acc
                     const int ai = pz * 2 * YT + 2 * y + py;
                     accs[ai].y_add = (int16_t)(y * G.LY * 2 + py);
                     accs[ai].z_add = (int8_t)pz;
+                    accs[ai].yl = (int8_t)(y * G.LY);
                     for (int ddy = 0; ddy <= py; ++ddy)
                         for (int ddz = 0; ddz <= pz; ++ddz) {
                             const int ky = py == 0 ? 1 : (ddy == 0 ? 2 : 0);
@@ -675,62 +712,73 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     const int sy_in = tr ? 1 : g->sy;
     // choose YT = number of y line groups per CTA
     const int ygroups = (Ym + LY - 1) / LY;   // a partial last group is zero-filled by TMA and masked in the epilogue
-    const int stages_total = (tr ? (3 * (in->C / 16) + 1) / 2 : (in->C / 16) * KX) + (src2 ? src2->C / 16 : 0);
-    int best = 0;
+    int best = 0, best_xt = 1;
     double best_cost = 1e30;
     size_t best_stage = 0;
     int best_nstage = 0;
     const int taps_stage = KY * KZ;
     const uint32_t b_bytes = (uint32_t)(2 * taps_stage * n_cta * 32);
-    const long total_tiles_1 = (long)in->B * Xm * (Zm / LZ) * (tr ? 2 : 1) * n_split;
-    for (int YT = 1; YT <= ygroups && YT <= 16; ++YT) {
-        if (ygroups % YT) continue;
-        if (YT * acc_mult * n_cta > 512) break;
-        if (YT * acc_mult > TC_MAX_ACC) break;
-        int nbox, BY, BZ;
-        if (line) { nbox = 1; BY = tr ? YT + 1 : (YT - 1) * sy_in + KY; BZ = LZ + 2 * hz; }
-        else if (tr) { nbox = g->sz; BY = YT * LY + 1; BZ = LZ; }
-        else if (strided) { nbox = KY * KZ; BY = YT * LY; BZ = LZ; }
-        else { nbox = KZ; BY = YT * LY + 2 * hy; BZ = LZ; }
-        if (!line && (BY * (strided ? g->sy : 1) > 256 || BZ * (strided ? g->sz : 1) > 256)) break;
-        const size_t box_bytes = (size_t)2 * BY * BZ * 16;
-        const size_t a_plane = round_up((int)(nbox * box_bytes), 128);
-        double mma_cyc = 0;
-        {
-            TcGeom G{tr, strided, line, KY, KZ, LY, LZ, BZ, (int)g->sz, n_cta, sy_in, (uint32_t)box_bytes,
-                     (uint32_t)a_plane, b_bytes / 2};
-            static TcOp scratch[TC_MAX_OPS];
-            static TcAcc scratch_acc[TC_MAX_ACC];
-            int n1 = 0, n2 = 0;
-            if (!gen_ops(G, YT, scratch, &n1, scratch_acc, &n2) || (src2 && YT * 3 > TC_MAX_OPS2)) break;
-            for (int i = 0; i < n1; ++i) {   // SS-mode MMA cost, measured (tools/ubench/mma_rate.cu)
-                const double N = scratch[i].n8 * 8.0;
-                mma_cyc += N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
+    // XT > 1 (several x rows per tile, stages = haloed x planes) cuts the 3x re-read of every input plane
+    // through L2; only for stride-1 convs with x taps, and only while a stage's weights stay small
+    const bool xt_ok = !tr && !strided && KX == 3 && (size_t)KX * b_bytes <= 40 * 1024;
+    static const int xt_max = getenv("VSSEG_TC_XT_MAX") ? atoi(getenv("VSSEG_TC_XT_MAX")) : 1;   // tuning knobs (measured: XT > 1 does not pay, the epilogue is the bottleneck)
+    static const int yt_max = getenv("VSSEG_TC_YT_MAX") ? atoi(getenv("VSSEG_TC_YT_MAX")) : 16;
+    for (int XT = 1; XT <= (xt_ok ? xt_max : 1); XT *= 2) {
+        if (Xm % XT) break;
+        const int npl = XT > 1 ? XT + KX - 1 : (tr ? 2 : KX);
+        const int stages_total = (tr ? (3 * (in->C / 16) + 1) / 2 : (in->C / 16) * npl) + (src2 ? (src2->C / 16) * XT : 0);
+        const size_t bstage = round_up((int)((XT > 1 ? KX : 1) * b_bytes), 128);
+        const long total_tiles_1 = (long)in->B * (Xm / XT) * (Zm / LZ) * (tr ? 2 : 1) * n_split;
+        for (int YT = 1; YT <= ygroups && YT <= yt_max; ++YT) {
+            if (ygroups % YT) continue;
+            if (XT * YT * acc_mult * n_cta > 512) break;
+            if (YT * acc_mult > TC_MAX_ACC) break;
+            int nbox, BY, BZ;
+            if (line) { nbox = 1; BY = tr ? YT + 1 : (YT - 1) * sy_in + KY; BZ = LZ + 2 * hz; }
+            else if (tr) { nbox = g->sz; BY = YT * LY + 1; BZ = LZ; }
+            else if (strided) { nbox = KY * KZ; BY = YT * LY; BZ = LZ; }
+            else { nbox = KZ; BY = YT * LY + 2 * hy; BZ = LZ; }
+            if (!line && (BY * (strided ? g->sy : 1) > 256 || BZ * (strided ? g->sz : 1) > 256)) break;
+            const size_t box_bytes = (size_t)2 * BY * BZ * 16;
+            const size_t a_plane = round_up((int)(nbox * box_bytes), 128);
+            double mma_cyc = 0;
+            {
+                TcGeom G{tr, strided, line, KY, KZ, LY, LZ, BZ, (int)g->sz, n_cta, sy_in, (uint32_t)box_bytes,
+                         (uint32_t)a_plane, b_bytes / 2};
+                static TcOp scratch[TC_MAX_OPS];
+                static TcAcc scratch_acc[TC_MAX_ACC];
+                int n1 = 0, n2 = 0;
+                if (!gen_ops(G, YT, scratch, &n1, scratch_acc, &n2) || (src2 && YT * 3 > TC_MAX_OPS2)) break;
+                for (int i = 0; i < n1; ++i) {   // SS-mode MMA cost, measured (tools/ubench/mma_rate.cu)
+                    const double N = scratch[i].n8 * 8.0;
+                    mma_cyc += N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
+                }
+                if (XT > 1) mma_cyc *= 3.0 * XT / (XT + 2);   // x taps served per plane stage, on average
             }
-        }
-        const size_t stage = 2 * a_plane + round_up((int)b_bytes, 128);
-        if (stage / 16 >= 16000) break;
-        const long budget = 227L * 1024 - TC_HDR;
-        int nst = (int)(budget / (long)stage);
-        if (nst < 2) break;
-        // cost model (persistent CTAs, one per SM): tiles per SM x tile time; tile time = main loop
-        // (stages x max(MMA cycles, smem fill at ~32 B/cycle/SM)) and epilogue, overlapped when the
-        // accumulators can be double-buffered in TMEM, serialised (plus pipeline refill) when not
-        const long tiles = total_tiles_1 * (ygroups / YT);
-        const bool dbuf = YT * acc_mult * n_cta <= 256;
-        const double fill_cyc = (double)stage / 32.0;
-        const double stage_cyc = mma_cyc > fill_cyc ? mma_cyc : fill_cyc;
-        const double main_cyc = stages_total * stage_cyc;
-        const double epi_cyc = 300.0 + YT * nphase * (n_cta / 16) * 260.0;
-        const double tile_cyc = dbuf ? (main_cyc > epi_cyc ? main_cyc : epi_cyc) + 200.0 : main_cyc + epi_cyc + 1500.0;
-        const double cost = (double)((tiles + 147) / 148) * tile_cyc + 4000.0;
-        if (cost < best_cost) {
-            best_cost = cost; best = YT; best_stage = stage;
-            best_nstage = nst > 6 ? 6 : nst;
+            const size_t stage = 2 * a_plane + bstage;
+            if (stage / 16 >= 16000) break;
+            const long budget = 227L * 1024 - TC_HDR;
+            int nst = (int)(budget / (long)stage);
+            if (nst < 2) break;
+            // cost model (persistent CTAs, one per SM): tiles per SM x tile time; tile time = main loop
+            // (stages x max(MMA cycles, smem fill at ~32 B/cycle/SM)) and epilogue, overlapped when the
+            // accumulators can be double-buffered in TMEM, serialised (plus pipeline refill) when not
+            const long tiles = total_tiles_1 * (ygroups / YT);
+            const bool dbuf = XT * YT * acc_mult * n_cta <= 256;
+            const double fill_cyc = (double)stage / 32.0;
+            const double stage_cyc = mma_cyc > fill_cyc ? mma_cyc : fill_cyc;
+            const double main_cyc = stages_total * stage_cyc;
+            const double epi_cyc = 300.0 + XT * YT * nphase * (n_cta / 16) * 260.0;
+            const double tile_cyc = dbuf ? (main_cyc > epi_cyc ? main_cyc : epi_cyc) + 200.0 : main_cyc + epi_cyc + 1500.0;
+            const double cost = (double)((tiles + 147) / 148) * tile_cyc + 4000.0;
+            if (cost < best_cost) {
+                best_cost = cost; best = YT; best_xt = XT; best_stage = stage;
+                best_nstage = nst > 6 ? 6 : nst;
+            }
         }
     }
     if (!best) return false;
-    const int YT = best;
+    const int YT = best, XT = best_xt;
     int nbox, BY, BZ;
     if (line) { nbox = 1; BY = tr ? YT + 1 : (YT - 1) * sy_in + KY; BZ = LZ + 2 * hz; }
     else if (tr) { nbox = g->sz; BY = YT * LY + 1; BZ = LZ; }
@@ -756,7 +804,8 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     a.lbo_b2 = (uint32_t)(n_cta * 16);
     const TcGeom G{tr, strided, line, KY, KZ, LY, LZ, BZ, (int)g->sz, n_cta, sy_in, box_bytes, a.a_plane, a.b_plane};
     a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);   // N field (bits 17..22) comes from the op
-    a.ntz = Zm / LZ; a.nty = ygroups / YT; a.ntx = Xm;
+    a.ntz = Zm / LZ; a.nty = ygroups / YT; a.ntx = Xm / XT;
+    a.XT = XT; a.npl = XT > 1 ? XT + KX - 1 : (tr ? 2 : KX);
     a.npx = tr ? 2 : 1; a.nsplit = n_split; a.nsel = a.npx * n_split;
     a.LZ = LZ; a.LY = LY; a.YL = YT * LY; a.Ym = Ym;
     a.n_cta = n_cta; a.cout = out->C;
@@ -799,7 +848,7 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
                 TcOp& op = a.ops2[n2++];
                 op.a16 = (uint16_t)(aoff / 16 + (pass == 1 ? a.a_plane / 16 : 0));
                 op.b16 = (uint16_t)(pass == 2 ? a.b2_plane / 16 : 0);
-                op.col = (uint16_t)((nacc + y) * n_cta);
+                op.col = (uint16_t)(y * n_cta);   // relative to the shortcut accumulators of the stage's x row
                 op.n8 = (uint16_t)(n_cta / 8);
             }
         }
@@ -809,7 +858,7 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     }
     a.ntiles = (int)((long)in->B * a.ntx * a.nty * a.ntz * a.nsel);
     const int sms = sm_count();
-    const int cols1 = nacc * (src2 ? 2 : 1) * n_cta;
+    const int cols1 = XT * nacc * (src2 ? 2 : 1) * n_cta;
     a.nbuf = (cols1 <= 256 && a.ntiles > sms) ? 2 : 1;   // double-buffered accumulators when a CTA walks several tiles
     const int cols = cols1 * a.nbuf;
     a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
@@ -914,7 +963,7 @@ int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, c
 
 int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
                            const vsseg_epilogue* ep, const float* sw_weight, void* stream) {
-    VSSEG_REQUIRE(in && out && out->ptr && out->C >= 1 && out->C <= 16, "conv3d_tc_f32out: Cout must be 1..16");
+    VSSEG_REQUIRE(in && out && out->ptr && out->C >= 1 && out->C <= 2, "conv3d_tc_f32out: Cout must be 1 or 2");
     // the plan only needs the output extents: describe the planar output as a 16-channel act8 tensor
     vsseg_act8 o16{};
     o16.hi = out->ptr; o16.B = out->B; o16.C = 16; o16.X = out->X; o16.Y = out->Y; o16.Z = out->Z;
