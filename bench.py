@@ -174,6 +174,7 @@ def main():
 
     import torch.distributed as dist
     from vs_seg_b200 import lib as vlib
+    from vs_seg_b200 import parallel as par
     from vs_seg_b200 import sliding_window as sw
     from vs_seg_b200.tensors import f32view
 
@@ -189,7 +190,6 @@ def main():
     net, sd = build_net(dev)
     predictor = lambda t: net(t)[0]  # noqa: E731
     predictor.native_model = net
-    shard = (rank, world) if world > 1 else None
 
     host = [synth_volume(i) for i in range(N_ROT)]
     pinned = [(v.pin_memory(), l.pin_memory()) for v, l in host]
@@ -199,13 +199,9 @@ def main():
     sums_host = torch.empty((1, 3), dtype=torch.float64).pin_memory()
 
     def infer(vol, label):
-        acc, cnt, lows, img = sw.sliding_window_accumulate(vol, ROI, predictor, 0.25, "gaussian",
-                                                           window_shard=shard)
-        if world > 1:
-            dist.reduce(acc, dst=0)
-            if rank != 0:
-                return None
-        return sw.finalize(acc, cnt, lows, img, label=label, return_mask=True)
+        # windows sharded by index over the ranks, one NCCL reduce of the accumulator to rank 0
+        return par.sharded_sliding_window_inference(vol, ROI, 1, predictor, 0.25, "gaussian", label=label,
+                                                    return_mask=True)
 
     def step_resident(i):
         v, l = vols[i % N_ROT]

@@ -1,0 +1,60 @@
+"""N>1 path on CPU: two gloo ranks shard the sliding-window windows and reduce the accumulator;
+the result must equal the single-process result (and the oracle)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sw_oracle
+
+
+def _predictor(x):
+    # a cheap stand-in network with 2 output channels and a spatial footprint (so blending matters)
+    k = torch.ones(2, 1, 3, 3, 3) / 27.0
+    k[1] *= -0.5
+    return torch.nn.functional.conv3d(x, k, padding=1) + x
+
+
+_predictor.out_channels = 2
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vs_seg_b200.parallel import sharded_sliding_window_inference
+    x = torch.randn((1, 1, 40, 36, 20), generator=torch.Generator().manual_seed(3))
+    res = sharded_sliding_window_inference(x, (16, 16, 8), 1, _predictor, mode="gaussian")
+    if rank == 0:
+        torch.save(res, out)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    from vs_seg_b200.sliding_window import shard_range, sliding_window_inference
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    x = torch.randn((1, 1, 40, 36, 20), generator=torch.Generator().manual_seed(3))
+    single = sliding_window_inference(x, (16, 16, 8), 1, _predictor, mode="gaussian")
+    ref = sw_oracle.sliding_window_inference(x, (16, 16, 8), 1, _predictor, mode="gaussian")
+    assert got.shape == ref.shape
+    assert (got - single).abs().max().item() < 1e-5
+    assert (got - ref).abs().max().item() < 1e-5
+    # the shards tile the window list exactly once
+    for n, w in [(32, 8), (32, 3), (5, 8), (1, 2)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
