@@ -165,6 +165,29 @@ int vsseg_att_gate(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_ac
 int vsseg_sw_finalize(const float* acc, const float* cnt, float* out, int32_t C, int64_t n,
                       uint8_t* mask, const float* label, double* sums, void* stream);
 
+/* ---- Dice_spvPA loss (reference params/losses/dice_spvPA.py:90-167, :238-297) -----------------------
+ * All tensors planar fp32, contiguous.  The loss is assembled from "terms": the 2-class logits term
+ * (softmax + one-hot + hardness weight w = lambda*|p - t| + 1 - lambda, gradient flowing through w) and
+ * one single-channel term per attention level against the max-pooled label.
+ *   vsseg_maxpool3d      label pyramid G_{l+1} = MaxPool3d(kernel = stride = ratio)(G_l)   (:268-277)
+ *   vsseg_dice_sums      C == 1: sums[b][0..2]    += (sum a*g, sum g, sum a)               (:136-149)
+ *                        C == 2: sums[b][c][0..2] += (sum w t_c p_c, sum w t_c, sum w p_c), p = softmax(logits),
+ *                                t = one_hot(label); hardness_lambda < 0 disables the weight (w = 1)
+ *   vsseg_dice_finalize  loss = sum_r row_scale[r] * (1 - (2I+smooth)/(G+P+smooth))         (:156-159, :295-297)
+ *                        coef[r] = row_scale[r] * (-2/D, (2I+smooth)/D^2), D = G+P+smooth   (backward factors)
+ *   vsseg_dice_backward  C == 1: grad = go * (alpha*g + beta); C == 2: d loss / d logits through the softmax
+ *                        Jacobian and the hardness weight; grad_out is the DEVICE scalar d(total)/d(loss).
+ * sums must be zeroed by the caller; fp64 accumulators. */
+int vsseg_maxpool3d(const float* in, float* out, int32_t B, int32_t Xo, int32_t Yo, int32_t Zo,
+                    int32_t rx, int32_t ry, int32_t rz, void* stream);
+int vsseg_dice_sums(const float* pred, const float* target, int32_t B, int32_t C, int64_t n,
+                    float hardness_lambda, double* sums, void* stream);
+int vsseg_dice_finalize(const double* sums, const float* row_scale, int32_t nrows, float smooth,
+                        float* loss, float* coef, void* stream);
+int vsseg_dice_backward(const float* pred, const float* target, int32_t B, int32_t C, int64_t n,
+                        float hardness_lambda, const float* coef, const float* grad_out, float* grad,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

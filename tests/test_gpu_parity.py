@@ -268,3 +268,68 @@ def test_tcgen05_fused_shortcut(B, cin, csrc, cout, dims, k):
                                require_tc=True).cpu()
     err = (got - ref).abs().max().item()
     assert err < 5e-5 * max(1.0, ref.abs().max().item()), err
+
+
+# ---- Dice_spvPA loss: native kernels vs the oracle (values and gradients) ---------------------------
+def _loss_inputs(B, dims, seed, empty=False, full=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((B, 2) + dims, generator=g)
+    t = (torch.rand((B, 1) + dims, generator=g) > 0.8).float()
+    if empty:
+        t.zero_()
+    if full:
+        t.fill_(1.0)
+    ratios = [(1, 1, 1), (2, 2, 1), (4, 4, 1), (8, 8, 2), (16, 16, 4), (32, 32, 8)]
+    atts = [torch.rand((B, 1) + tuple(d // r for d, r in zip(dims, rr)), generator=g) for rr in reversed(ratios)]
+    return x, t, atts
+
+
+@pytest.mark.parametrize("B,dims,sup,hard,kind", [
+    (2, (32, 32, 8), True, True, "mixed"), (1, (64, 32, 16), True, True, "mixed"), (2, (32, 32, 8), False, True, "mixed"),
+    (1, (32, 32, 8), True, False, "mixed"), (1, (32, 64, 8), True, True, "empty"), (1, (32, 32, 8), True, True, "full"),
+])
+def test_dice_spvpa_native_matches_oracle(B, dims, sup, hard, kind):
+    from params.losses.dice_spvPA import Dice_spvPA
+    dev = _dev()
+    x, t, atts = _loss_inputs(B, dims, 7, empty=kind == "empty", full=kind == "full")
+    xr = x.double().requires_grad_(True)
+    ar = [a.double().requires_grad_(True) for a in atts]
+    ref = loss_oracle.dice_spvpa_loss(xr, ar, t.double(), sup, hard)
+    (ref * 1.7).backward()
+    xg = x.to(dev).requires_grad_(True)
+    ag = [a.to(dev).requires_grad_(True) for a in atts]
+    crit = Dice_spvPA(to_onehot_y=True, softmax=True, supervised_attention=sup, hardness_weighting=hard)
+    got = crit((xg, ag), t.to(dev))
+    (got * 1.7).backward()
+    assert abs(got.item() - ref.item()) < 2e-6 * max(1.0, abs(ref.item()))
+    scale = xr.grad.abs().max().item()
+    assert (xg.grad.cpu().double() - xr.grad).abs().max().item() < 1e-5 * scale + 1e-12
+    for a_g, a_r in zip(ag, ar):
+        if sup:
+            assert (a_g.grad.cpu().double() - a_r.grad).abs().max().item() < 1e-5 * a_r.grad.abs().max().item() + 1e-12
+        else:
+            assert a_g.grad is None and a_r.grad is None
+
+
+@pytest.mark.parametrize("case", ["ellipsoid", "empty", "full"])
+def test_dice_spvpa_native_matches_reference_golden(golden_dir, case):
+    """Loss values (all four flag combinations) and gradients produced by the unmodified reference
+    loss (tests/golden/dice_spvpa_loss.npz, generated by oracle/make_golden.py)."""
+    from params.losses.dice_spvPA import Dice_spvPA
+    g = np.load(os.path.join(golden_dir, "dice_spvpa_loss.npz"))
+    dev = _dev()
+    y = torch.from_numpy(g[f"{case}_y"]).to(dev)
+    for sup in (1, 0):
+        for hard in (1, 0):
+            x = torch.from_numpy(g[f"{case}_x"]).to(dev).requires_grad_(True)
+            atts = [torch.from_numpy(g[f"{case}_att{i}"]).to(dev).requires_grad_(True) for i in range(6)]
+            crit = Dice_spvPA(to_onehot_y=True, softmax=True, supervised_attention=bool(sup), hardness_weighting=bool(hard))
+            loss = crit((x, atts), y)
+            assert abs(loss.item() - float(g[f"{case}_a{sup}h{hard}_loss"])) < 1e-5, (case, sup, hard)
+            if sup and hard:
+                loss.backward()
+                gx = g[f"{case}_gx"]
+                assert np.abs(x.grad.cpu().numpy() - gx).max() < 1e-5 * np.abs(gx).max() + 1e-10
+                for i in range(6):
+                    ga = g[f"{case}_gatt{i}"]
+                    assert np.abs(atts[i].grad.cpu().numpy() - ga).max() < 1e-5 * np.abs(ga).max() + 1e-10

@@ -58,6 +58,12 @@ _SIGNATURES = {
     "vsseg_conv3d_smallcout": (C.c_int, [_P(Act8), _P(F32View), _P(ConvGeom), C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_float, C.c_void_p, C.c_void_p]),
     "vsseg_att_gate": (C.c_int, [_P(Act8), _P(F32View), _P(Act8), C.c_void_p]),
+    "vsseg_maxpool3d": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
+    "vsseg_dice_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
+                                  C.c_void_p]),
+    "vsseg_dice_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsseg_dice_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsseg_sw_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
 }
