@@ -1,0 +1,90 @@
+"""Host plumbing on CPU (BASELINE config 0): NIfTI I/O, transforms, VSparams train + inference recipe on
+tiny synthetic volumes.  No GPU, no native kernels: the torch containers of the drop-in modules run."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+from vs_seg_b200 import dataio
+
+
+def test_nifti_roundtrip_and_orientation(tmp_path):
+    rng = np.random.RandomState(0)
+    vol = rng.standard_normal((5, 6, 7)).astype(np.float32)
+    aff = np.array([[-0.5, 0, 0, 10], [0, 0.5, 0, -3], [0, 0, 2.0, 4], [0, 0, 0, 1.0]])  # LAS: x flipped
+    p = str(tmp_path / "a.nii.gz")
+    dataio.write_nifti(p, vol, aff)
+    got, got_aff = dataio.read_nifti(p)
+    assert got.dtype == np.float32 and np.array_equal(got, vol) and np.allclose(got_aff, aff)
+    d = dataio.Compose([dataio.LoadNiftid(keys=["image"]), dataio.AddChanneld(keys=["image"]),
+                        dataio.Orientationd(keys=["image"], axcodes="RAS")])({"image": p})
+    assert np.array_equal(d["image"][0], vol[::-1])  # flipped to R
+    assert d["image_meta_dict"]["affine"][0, 0] > 0
+    lab = (vol > 0).astype(np.uint8)
+    dataio.write_nifti(str(tmp_path / "l.nii"), lab, aff)
+    got_l, _ = dataio.read_nifti(str(tmp_path / "l.nii"))
+    assert got_l.dtype == np.uint8 and np.array_equal(got_l, lab)
+
+
+def test_transforms_pad_crop_flip_cache():
+    item = {"image": np.arange(2 * 3 * 4, dtype=np.float32).reshape(1, 2, 3, 4), "label": np.ones((1, 2, 3, 4), np.float32)}
+    pad = dataio.SpatialPadd(keys=["image", "label"], spatial_size=[5, 3, 8])(item)
+    assert pad["image"].shape == (1, 5, 3, 8) and pad["label"].sum() == 24
+    assert pad["image"][0, 1, 0, 2] == 0.0  # symmetric: 1 before / 2 after in x, 2/2 in z
+    crop = dataio.RandSpatialCropd(keys=["image", "label"], roi_size=[2, 2, 2]).set_random_state(seed=1)(pad)
+    assert crop["image"].shape == (1, 2, 2, 2)
+    norm = dataio.NormalizeIntensityd(keys=["image"])(item)["image"]
+    assert abs(norm.mean()) < 1e-6 and abs(norm.std() - 1) < 1e-6
+    chain = dataio.Compose([dataio.NormalizeIntensityd(keys=["image"]),
+                            dataio.RandFlipd(keys=["image", "label"], prob=1.0, spatial_axis=0),
+                            dataio.ToTensord(keys=["image", "label"])])
+    ds = dataio.CacheDataset([item], chain)
+    assert chain.first_random_index() == 1
+    out = ds[0]
+    assert torch.is_tensor(out["image"]) and torch.equal(out["image"], torch.from_numpy(norm[:, ::-1].copy()))
+
+
+def test_vsparams_train_and_inference_recipe_on_cpu(tmp_path, monkeypatch):
+    """The call order of VS_train.py / VS_inference.py on 6 synthetic 48x56x12 cases padded/cropped to 64x64x16, 2 epochs."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.chdir(root)
+    from params.VSparams import VSparams
+    data_root = str(tmp_path / "VS_defaced") + "/"
+    monkeypatch.setattr(sys, "argv", ["VS_train.py", "--debug", "--dataset", "T1", "--device", "cpu", "--synthetic",
+                                      "--num_epochs", "2", "--data_root", data_root])
+    p = VSparams(argparse.ArgumentParser())
+    p.num_workers = 0
+    p.synthetic_shape = (48, 56, 12)   # smaller than the crop: exercises SpatialPadd and the inferer's padding
+    p.pad_crop_shape = p.pad_crop_shape_test = p.sliding_window_inferer_roi_size = [64, 64, 16]
+    p.create_results_folders()
+    p.set_up_logger("training_log.txt")
+    p.log_parameters()
+    train_files, val_files, test_files = p.load_T1_or_T2_data()
+    assert (len(train_files), len(val_files), len(test_files)) == (2, 2, 2)
+    train_t, val_t, test_t = p.get_transforms()
+    dataio.set_determinism(seed=0)
+    p.check_transforms_on_first_validation_image_and_label(val_files, val_t)
+    train_loader = p.cache_transformed_train_data(train_files, train_t)
+    val_loader = p.cache_transformed_val_data(val_files, val_t)
+    model = p.set_and_get_model()
+    assert len(model.state_dict()) == 256
+    losses, metrics = p.run_training_algorithm(model, p.set_and_get_loss_function(), p.set_and_get_optimizer(model),
+                                               train_loader, val_loader)
+    assert len(losses) == 2 and len(metrics) == 1 and all(np.isfinite(losses))
+    p.plot_loss_curve_and_mean_dice(losses, metrics)
+    for f in ("best_metric_model.pth", "last_epoch_model.pth"):
+        assert os.path.isfile(os.path.join(p.model_path, f))
+    # inference recipe
+    test_loader = p.cache_transformed_test_data(test_files, test_t)
+    model = p.load_trained_state_of_model(p.set_and_get_model())
+    scores = p.run_inference(model, test_loader)
+    assert scores.shape == (2,) and np.all((scores >= 0) & (scores <= 1))
+    out = os.path.join(p.results_folder_path, "inferred_segmentations_nifti", "vs_gk_202", "vs_gk_seg_refT1",
+                       "vs_gk_seg_refT1.nii.gz")
+    assert os.path.isfile(out)
+    seg, _ = dataio.read_nifti(out)
+    assert seg.shape == (48, 56, 12) and set(np.unique(seg)) <= {0, 1}
+    for h in list(p.logger.handlers):
+        p.logger.removeHandler(h)
