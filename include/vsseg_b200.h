@@ -188,6 +188,46 @@ int vsseg_dice_backward(const float* pred, const float* target, int32_t B, int32
                         float hardness_lambda, const float* coef, const float* grad_out, float* grad,
                         void* stream);
 
+/* ---- training mode (reference convolutions.py:148-156 Conv -> BatchNorm3d -> Dropout -> PReLU, autograd) -----
+ * Convolutions (forward and data gradient) use vsseg_conv3d_tc: the data gradient of a Conv3d is the
+ * ConvTranspose3d with the same weight tensor and vice versa.  The entry points below are the pieces around it.
+ *   stats layout: float [4][C] = scale (gamma*rstd) | shift (beta - mean*scale) | batch mean | rstd
+ *   vsseg_bn_stats           sums[0][C] += sum x, sums[1][C] += sum x^2 over (B,X,Y,Z)      (fp64, zeroed by the caller)
+ *   vsseg_bn_finalize        batch mean / BIASED variance -> stats; running_mean/var <- (1-m)*old + m*(mean / UNBIASED var)
+ *   vsseg_bn_act_fwd         y = PReLU_slope(dropout_p(c*scale + shift)) [+ residual]; dropout mask = hash(seed, element)
+ *   vsseg_bn_act_bwd_reduce  sums[0][C] += sum du, sums[1][C] += sum du*xhat, sums[2C] += d(slope)   (du = grad after
+ *                            PReLU' and the dropout mask)
+ *   vsseg_bn_act_bwd_apply   dc = scale * (du - mean(du) - xhat*mean(du*xhat))
+ *   vsseg_act_bwd            dc = dy * (y > 0 ? 1 : slope)                                   (attention conv1 ReLU)
+ *   vsseg_act8_add           out = a + b                                                     (fan-out gradient sums)
+ *   vsseg_conv3d_wgrad       dw[tap][Cin][cout_pad] += sum x[v_in]*dc[v_out], dbias[c] += sum dc  (fp32 atomics; both
+ *                            zeroed by the caller; geometry as the forward conv, transposed included)
+ *   vsseg_conv3d_cin1_wgrad  same for the 1-channel fp32 source of the first conv / its 1x1x1 shortcut; dw[tap][Cout]
+ *   vsseg_conv3d_smallcout_bwd  backward of vsseg_conv3d_smallcout (Cout 1|2): dz = dy*(sigmoid ? y(1-y) : 1);
+ *                            dx (act8, optional), dw[tap][Cin][Cout] and dbias (optional, accumulated)
+ *   vsseg_att_gate_bwd       g = x*(1+att): dx = dg*(1+att) (+ dx if accumulate_dx), datt = sum_c dg_c*x_c */
+int vsseg_bn_stats(const vsseg_act8* x, double* sums, void* stream);
+int vsseg_bn_finalize(const double* sums, int32_t C, int64_t count, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, float* stats,
+                      void* stream);
+int vsseg_bn_act_fwd(const vsseg_act8* c, const vsseg_act8* y, const float* stats, float slope, float drop_p,
+                     uint64_t seed, const vsseg_act8* residual, void* stream);
+int vsseg_bn_act_bwd_reduce(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, float slope,
+                            float drop_p, uint64_t seed, double* sums, void* stream);
+int vsseg_bn_act_bwd_apply(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const double* sums,
+                           float slope, float drop_p, uint64_t seed, const vsseg_act8* dc, void* stream);
+int vsseg_act_bwd(const vsseg_act8* y, const vsseg_act8* dy, float slope, const vsseg_act8* dc, void* stream);
+int vsseg_act8_add(const vsseg_act8* a, const vsseg_act8* b, const vsseg_act8* out, void* stream);
+int vsseg_conv3d_wgrad(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_conv_geom* g, float* dw,
+                       int32_t cout_pad, float* dbias, void* stream);
+int vsseg_conv3d_cin1_wgrad(const vsseg_f32view* src, const vsseg_act8* dc, const vsseg_conv_geom* g,
+                            float* dw, float* dbias, void* stream);
+int vsseg_conv3d_smallcout_bwd(const vsseg_act8* x, const vsseg_f32view* dy, const vsseg_f32view* y,
+                               const vsseg_conv_geom* g, const float* w, int32_t sigmoid,
+                               const vsseg_act8* dx, float* dw, float* dbias, void* stream);
+int vsseg_att_gate_bwd(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_act8* dg,
+                       const vsseg_act8* dx, const vsseg_f32view* datt, int32_t accumulate_dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

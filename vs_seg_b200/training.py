@@ -1,8 +1,492 @@
-"""Native training path (forward with batch statistics + backward kernels).  Not built yet: the
-CUDA train-mode forward raises instead of silently running eager torch."""
+"""Train-mode forward and backward of UNet2d5_spvPA on the native kernels (no torch/cuDNN compute).
+
+Mirrors the module tree of the reference (/root/reference/params/networks/nets/unet2d5_spvPA.py:56-202)
+as a tape of native launches:
+
+  Convolution (convolutions.py:148-156, Conv -> BatchNorm3d -> Dropout -> PReLU)
+      conv (tcgen05 kernel, bias in the epilogue) -> bn_stats -> bn_finalize (batch mean / biased var,
+      running-stat update) -> bn_act_fwd (normalise + dropout + PReLU [+ ResidualUnit shortcut])
+      backward: bn_act_bwd_reduce -> bn_act_bwd_apply -> conv3d_wgrad (+ bias grad) -> data gradient =
+      the adjoint convolution on the SAME tcgen05 kernel (Conv3d <-> ConvTranspose3d with the same weights)
+  AttentionBlock1/2 (attentionblock.py:10-47): conv+ReLU, conv+Sigmoid, gate x*(1+att) and their backward
+  SkipConnection: channel views of one buffer (forward) / of one gradient buffer (backward)
+
+torch only owns memory, provides the autograd boundary (`_UNetTrainFn`) and sums two 1-channel
+attention-map gradients; parameters stay the module's own tensors, so torch.optim.Adam applies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+from .engine import _round_up, pack_conv_weight, pack_conv_weight_tc
+from .tensors import Act8Buffer, f32view
+
+_BN_EPS, _BN_MOM = 1e-5, 0.1
+
+
+class _GradBuf:
+    """Gradient of an activation tensor: first writer stores, later writers accumulate."""
+
+    def __init__(self, like: Act8Buffer):
+        self.buf = Act8Buffer(like.B, like.C, like.X, like.Y, like.Z, like.device)
+        self.filled = False
+
+
+class UNetTrainStep:
+    def __init__(self, model, x: torch.Tensor):
+        self.lib = _lib.load()
+        self.m = model
+        self.dev = x.device
+        self.B = x.shape[0]
+        self.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        self.tape = []
+        self.keep = []
+        self.pgrads = {}          # parameter name -> fp32 grad tensor (torch layout)
+        self.p = dict(model.named_parameters())
+        self.bufs = dict(model.named_buffers())
+        self.drop_p = float(model.dropout or 0.0)
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.layer_id = 0
+
+    # ---- small helpers --------------------------------------------------------------------------------
+    def _chk(self, code, what):
+        if code:
+            _lib.check(code, what)
+        _lib.count_launch()
+
+    def _buf(self, C_, dims):
+        b = Act8Buffer(self.B, C_, dims[0], dims[1], dims[2], self.dev)
+        self.keep.append(b)
+        return b
+
+    def _geom(self, k, s=(1, 1, 1), transposed=False):
+        return _lib.ConvGeom(k[0], k[1], k[2], s[0], s[1], s[2], 1 if transposed else 0)
+
+    def _addgrad(self, name, g):
+        g = g.reshape(self.p[name].shape).to(self.p[name].dtype)
+        self.pgrads[name] = g if name not in self.pgrads else self.pgrads[name] + g
+
+    def _ident_ep(self, bias, cpad):
+        scale = torch.ones(cpad, device=self.dev)
+        shift = torch.nn.functional.pad(bias.detach().float(), (0, cpad - bias.numel()))
+        self.keep += [scale, shift]
+        return scale, shift
+
+    # ---- convolution launches -------------------------------------------------------------------------
+    def _conv(self, src, dst, geom, w_conv_layout, transposed, scale, shift, slope=1.0, act=0, res=None):
+        """dst = act(conv(src)*scale + shift) [+ res]; w in torch layout (Conv3d, or ConvTranspose3d if transposed)."""
+        cpad = _round_up(dst.C, 16)
+        ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, act)
+        res_p = C.byref(res) if res is not None else None
+        ns = 0
+        if src.C % 16 == 0:
+            ns = self.lib.vsseg_conv3d_tc_suggest_split(C.byref(src), C.byref(dst), C.byref(geom), None)
+        w_conv_layout = _pad_cin(w_conv_layout, transposed, src.C)   # zero weights for zero-padded input channels
+        if ns > 0:
+            w = pack_conv_weight_tc(_pad_cout(w_conv_layout, transposed, dst.C), transposed, ns)
+            self.keep.append(w)
+            self._chk(self.lib.vsseg_conv3d_tc(C.byref(src), C.byref(dst), C.byref(geom), w.data_ptr(), ns, C.byref(ep),
+                                               res_p, None, None, None, None, None, None, self.stream), "conv3d_tc")
+        else:
+            w = pack_conv_weight(w_conv_layout, transposed, cpad)
+            self.keep.append(w)
+            self._chk(self.lib.vsseg_conv3d_act8(C.byref(src), C.byref(dst), C.byref(geom), w.data_ptr(), cpad, C.byref(ep),
+                                                 res_p, None, None, None, self.stream), "conv3d_act8")
+
+    def _dgrad(self, dc, w, k, stride, transposed, gx: _GradBuf, c0=0, Cx=None):
+        """Data gradient of a (transposed) conv = its adjoint convolution with the same weights."""
+        dx = gx.buf.view(c0, Cx)
+        cpad = _round_up(dx.C, 16)
+        scale = torch.ones(cpad, device=self.dev)
+        shift = torch.zeros(cpad, device=self.dev)
+        self.keep += [scale, shift]
+        acc = gx.filled
+        if not transposed and tuple(stride) == (1, 1, 1):
+            wd = w.detach().flip(2, 3, 4).transpose(0, 1).contiguous()      # Conv3d weight [Cin, Cout, k] of the adjoint
+            self._conv(dc, dx, self._geom(k), wd, False, scale, shift, res=dx if acc else None)
+        elif not transposed:
+            # strided Conv3d: adjoint = ConvTranspose3d whose weight tensor [in=Cout, out=Cin, k] is W itself
+            self._conv(dc, dx, self._geom(k, stride, True), w.detach(), True, scale, shift, res=dx if acc else None)
+        else:
+            # ConvTranspose3d [Cin, Cout, k]: adjoint = strided Conv3d with weight [out=Cin, in=Cout, k] = W itself
+            self._conv(dc, dx, self._geom(k, stride, False), w.detach(), False, scale, shift, res=dx if acc else None)
+        gx.filled = True
+
+    def _wgrad(self, x, dc, k, stride, transposed, wname, bname):
+        w = self.p[wname]
+        cout = w.shape[1] if transposed else w.shape[0]
+        cin = w.shape[0] if transposed else w.shape[1]
+        cpad = _round_up(dc.C, 16)
+        taps = k[0] * k[1] * k[2]
+        dw = torch.zeros((taps, x.C, cpad), device=self.dev)
+        db = torch.zeros(cpad, device=self.dev)
+        g = self._geom(k, stride, transposed)
+        self._chk(self.lib.vsseg_conv3d_wgrad(C.byref(x), C.byref(dc), C.byref(g), dw.data_ptr(), cpad, db.data_ptr(),
+                                              self.stream), "conv3d_wgrad")
+        dw = dw[:, :cin, :cout].reshape(k[0], k[1], k[2], cin, cout)
+        self._addgrad(wname, dw.permute(3, 4, 0, 1, 2) if transposed else dw.permute(4, 3, 0, 1, 2))
+        self._addgrad(bname, db[:cout])
+
+    # ---- blocks ---------------------------------------------------------------------------------------
+    def convolution(self, prefix, src, src_grad, dst, k, stride=(1, 1, 1), transposed=False, residual=None, cin1=None,
+                    c0=0, Cx=None):
+        """Conv -> BN(batch stats) -> Dropout -> PReLU [+ residual] into `dst` (an Act8 view).  src_grad: _GradBuf of the
+        input (None: input needs no gradient); (c0, Cx) channel range of `src` inside src_grad.
+        cin1: F32View of a 1-channel fp32 source (first conv) instead of `src`.  Returns a _GradBuf-less closure on the tape."""
+        lib, s = self.lib, self.stream
+        w, bias = self.p[prefix + "conv.weight"], self.p[prefix + "conv.bias"]
+        gamma, beta = self.p[prefix + "norm.weight"], self.p[prefix + "norm.bias"]
+        slope_t = self.p[prefix + "act.weight"]
+        slope = float(slope_t.detach().reshape(-1)[0])
+        Cc = dst.C
+        cbuf = Act8Buffer(dst.B, Cc, dst.X, dst.Y, dst.Z, self.dev)
+        self.keep.append(cbuf)
+        c = cbuf.view()
+        cpad = _round_up(Cc, 16)
+        scale, shift = self._ident_ep(bias, cpad)
+        geom = self._geom(k, stride, transposed)
+        if cin1 is not None:
+            wp = pack_conv_weight(w.detach(), False)[:, 0, :].contiguous()
+            ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), 1.0, 0)
+            self.keep += [wp]
+            self._chk(lib.vsseg_conv3d_cin1(C.byref(cin1), C.byref(c), C.byref(geom), wp.data_ptr(), C.byref(ep), s), "cin1")
+        else:
+            self._conv(src, c, geom, w.detach(), transposed, scale, shift)
+        count = dst.B * dst.X * dst.Y * dst.Z
+        sums = torch.zeros(2 * Cc, dtype=torch.float64, device=self.dev)
+        stats = torch.empty(4 * Cc, device=self.dev)
+        rm, rv = self.bufs[prefix + "norm.running_mean"], self.bufs[prefix + "norm.running_var"]
+        self._chk(lib.vsseg_bn_stats(C.byref(c), sums.data_ptr(), s), "bn_stats")
+        self._chk(lib.vsseg_bn_finalize(sums.data_ptr(), Cc, count, gamma.data_ptr(), beta.data_ptr(), _BN_EPS, _BN_MOM,
+                                        rm.data_ptr(), rv.data_ptr(), stats.data_ptr(), s), "bn_finalize")
+        self.bufs[prefix + "norm.num_batches_tracked"].add_(1)
+        self.layer_id += 1
+        seed = (self.seed + 0x1000003 * self.layer_id) & (2 ** 63 - 1)
+        res_p = C.byref(residual) if residual is not None else None
+        self._chk(lib.vsseg_bn_act_fwd(C.byref(c), C.byref(dst), stats.data_ptr(), slope, self.drop_p, seed, res_p, s), "bn_act_fwd")
+        self.keep += [sums, stats, c, dst, src, residual]
+
+        def backward(dy):
+            sums2 = torch.zeros(2 * Cc + 1, dtype=torch.float64, device=self.dev)
+            self._chk(lib.vsseg_bn_act_bwd_reduce(C.byref(c), C.byref(dy), stats.data_ptr(), slope, self.drop_p, seed,
+                                                  sums2.data_ptr(), s), "bn_act_bwd_reduce")
+            self._addgrad(prefix + "norm.bias", sums2[:Cc].float())
+            self._addgrad(prefix + "norm.weight", sums2[Cc:2 * Cc].float())
+            self._addgrad(prefix + "act.weight", sums2[2 * Cc:].float())
+            dcb = Act8Buffer(dst.B, Cc, dst.X, dst.Y, dst.Z, self.dev)
+            dc = dcb.view()
+            self._chk(lib.vsseg_bn_act_bwd_apply(C.byref(c), C.byref(dy), stats.data_ptr(), sums2.data_ptr(), slope, self.drop_p,
+                                                 seed, C.byref(dc), s), "bn_act_bwd_apply")
+            if cin1 is not None:
+                taps = k[0] * k[1] * k[2]
+                dw = torch.zeros((taps, Cc), device=self.dev)
+                db = torch.zeros(Cc, device=self.dev)
+                self._chk(lib.vsseg_conv3d_cin1_wgrad(C.byref(cin1), C.byref(dc), C.byref(geom), dw.data_ptr(), db.data_ptr(), s),
+                          "cin1_wgrad")
+                self._addgrad(prefix + "conv.weight", dw.reshape(k[0], k[1], k[2], 1, Cc).permute(4, 3, 0, 1, 2))
+                self._addgrad(prefix + "conv.bias", db)
+                return
+            self._wgrad(src, dc, k, stride, transposed, prefix + "conv.weight", prefix + "conv.bias")
+            if src_grad is not None:
+                self._dgrad(dc, w, k, stride, transposed, src_grad, c0, Cx)
+
+        return backward
+
+    def shortcut(self, prefix, src, src_grad, dst, cin1=None):
+        """1x1x1 ResidualUnit shortcut conv (convolutions.py:241-250) into `dst`; returns its backward."""
+        lib, s = self.lib, self.stream
+        w, bias = self.p[prefix + "weight"], self.p[prefix + "bias"]
+        cpad = _round_up(dst.C, 16)
+        scale, shift = self._ident_ep(bias, cpad)
+        geom = self._geom((1, 1, 1))
+        if cin1 is not None:
+            wp = pack_conv_weight(w.detach(), False)[:, 0, :].contiguous()
+            ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), 1.0, 0)
+            self.keep += [wp]
+            self._chk(lib.vsseg_conv3d_cin1(C.byref(cin1), C.byref(dst), C.byref(geom), wp.data_ptr(), C.byref(ep), s), "cin1")
+        else:
+            self._conv(src, dst, geom, w.detach(), False, scale, shift)
+
+        def backward(dy):
+            if cin1 is not None:
+                dw = torch.zeros((1, dst.C), device=self.dev)
+                db = torch.zeros(dst.C, device=self.dev)
+                self._chk(lib.vsseg_conv3d_cin1_wgrad(C.byref(cin1), C.byref(dy), C.byref(geom), dw.data_ptr(), db.data_ptr(), s),
+                          "cin1_wgrad")
+                self._addgrad(prefix + "weight", dw.reshape(1, 1, 1, 1, dst.C).permute(4, 3, 0, 1, 2))
+                self._addgrad(prefix + "bias", db)
+                return
+            self._wgrad(src, dy, (1, 1, 1), (1, 1, 1), False, prefix + "weight", prefix + "bias")
+            if src_grad is not None:
+                self._dgrad(dy, w, (1, 1, 1), (1, 1, 1), False, src_grad)
+
+        return backward
+
+    def residual_unit(self, prefix, src, src_grad, dst_buf, dst_c0, cout, k, subunits, cin1=None):
+        """ResidualUnit (convolutions.py:209-255): out = conv path + shortcut, written to dst_buf[dst_c0 : dst_c0+cout].
+        Returns backward(dout_view)."""
+        dims = (dst_buf.X, dst_buf.Y, dst_buf.Z)
+        sbuf = self._buf(cout, dims)
+        bw_sc = self.shortcut(prefix + "residual.", src, src_grad, sbuf.view(), cin1=cin1)
+        dst = dst_buf.view(dst_c0, cout)
+        if subunits == 2:
+            hbuf = self._buf(cout, dims)
+            gh = _GradBuf(hbuf)
+            bw0 = self.convolution(prefix + "conv.unit0.", src, src_grad, hbuf.view(), k, cin1=cin1)
+            bw1 = self.convolution(prefix + "conv.unit1.", hbuf.view(), gh, dst, k, residual=sbuf.view())
+
+            def backward(dout):
+                bw1(dout)
+                bw0(gh.buf.view())
+                bw_sc(dout)
+        else:
+            bw0 = self.convolution(prefix + "conv.unit0.", src, src_grad, dst, k, residual=sbuf.view())
+
+            def backward(dout):
+                bw0(dout)
+                bw_sc(dout)
+        return backward
+
+    def attention(self, prefix, xbuf: Act8Buffer, gx: _GradBuf, k):
+        """AttentionBlock1 + AttentionBlock2 on all channels of xbuf; returns (gated buffer, its _GradBuf, att tensor,
+        backward(datt_from_loss))."""
+        lib, s = self.lib, self.stream
+        Cc = xbuf.C
+        dims = (xbuf.X, xbuf.Y, xbuf.Z)
+        x = xbuf.view()
+        hC = _round_up(Cc // 2, 16)
+        hbuf = self._buf(hC, dims)
+        h = hbuf.view()
+        w1, b1 = self.p[prefix + "0.conv1.conv.weight"], self.p[prefix + "0.conv1.conv.bias"]
+        w2, b2 = self.p[prefix + "0.conv2.conv.weight"], self.p[prefix + "0.conv2.conv.bias"]
+        sc1, sh1 = self._ident_ep(b1, _round_up(hC, 16))
+        self._conv(x, h, self._geom(k), w1.detach(), False, sc1, sh1, slope=0.0)        # conv + ReLU
+        att = torch.empty((self.B, 1) + dims, device=self.dev)
+        av = f32view(att)
+        w2p = w2.detach().float()
+        if w2p.shape[1] != hC:
+            w2p = torch.nn.functional.pad(w2p, (0, 0, 0, 0, 0, 0, 0, hC - w2p.shape[1]))
+        w2g = pack_conv_weight(w2p, False)                                               # [taps][hC][1]
+        b2f = b2.detach().float().contiguous()
+        g2 = self._geom(k)
+        self._chk(lib.vsseg_conv3d_smallcout(C.byref(h), C.byref(av), C.byref(g2), w2g.data_ptr(), b2f.data_ptr(), 1, 0.0, None, s),
+                  "smallcout")
+        gbuf = self._buf(Cc, dims)
+        g = gbuf.view()
+        self._chk(lib.vsseg_att_gate(C.byref(x), C.byref(av), C.byref(g), s), "att_gate")
+        gg = _GradBuf(gbuf)
+        self.keep += [w2g, b2f, att, av, x, h, g]
+
+        def backward(datt_loss):
+            # gate: dx = dg*(1+att), datt = sum_c dg*x
+            datt = torch.empty_like(att)
+            dav = f32view(datt)
+            dx = gx.buf.view()
+            self._chk(lib.vsseg_att_gate_bwd(C.byref(x), C.byref(av), C.byref(gg.buf.view()), C.byref(dx), C.byref(dav),
+                                             1 if gx.filled else 0, s), "att_gate_bwd")
+            gx.filled = True
+            if datt_loss is not None:
+                datt = datt + datt_loss.reshape(datt.shape).float()
+                dav = f32view(datt)
+            # conv2 + sigmoid backward -> dh, dW2, db2
+            gh = _GradBuf(hbuf)
+            taps = k[0] * k[1] * k[2]
+            dw2 = torch.zeros((taps, hC, 1), device=self.dev)
+            db2 = torch.zeros(1, device=self.dev)
+            dh = gh.buf.view()
+            self._chk(lib.vsseg_conv3d_smallcout_bwd(C.byref(h), C.byref(dav), C.byref(av), C.byref(g2), w2g.data_ptr(), 1,
+                                                     C.byref(dh), dw2.data_ptr(), db2.data_ptr(), s), "smallcout_bwd")
+            cin2 = w2.shape[1]
+            self._addgrad(prefix + "0.conv2.conv.weight",
+                          dw2[:, :cin2, :].reshape(k[0], k[1], k[2], cin2, 1).permute(4, 3, 0, 1, 2))
+            self._addgrad(prefix + "0.conv2.conv.bias", db2)
+            # conv1 + ReLU backward
+            dcb = Act8Buffer(self.B, hC, *dims, self.dev)
+            dc = dcb.view()
+            self._chk(lib.vsseg_act_bwd(C.byref(h), C.byref(dh), 0.0, C.byref(dc), s), "act_bwd")
+            self._wgrad(x, dc, k, (1, 1, 1), False, prefix + "0.conv1.conv.weight", prefix + "0.conv1.conv.bias")
+            self._dgrad(dc, w1, k, (1, 1, 1), False, gx)
+            self.keep += [datt, dcb, gh]
+
+        return gbuf, gg, att, backward
+
+    # ---- whole network ----------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor):
+        m = self.m
+        lib, s = self.lib, self.stream
+        ch = tuple(m.channels)
+        nlev = len(ch)
+        strides = [tuple(v) for v in m.strides]
+        ks = [tuple(v) for v in m.kernel_sizes]
+        sks = [tuple(v) for v in m.sample_kernel_sizes]
+        att_on = bool(m.attention_module)
+        dims = [tuple(x.shape[2:])]
+        for st in strides:
+            dims.append(tuple(d // q for d, q in zip(dims[-1], st)))
+        xin = x.detach().float().contiguous()
+        self.keep.append(xin)
+        xv = f32view(xin)
+        cat = [self._buf(2 * ch[l], dims[l]) for l in range(nlev - 1)]
+        gcat = [_GradBuf(cb) for cb in cat]
+        dn = [self._buf(ch[l], dims[l + 1]) for l in range(nlev - 1)]
+        gdn = [_GradBuf(b) for b in dn]
+        prefixes, p = [], "model."
+        for l in range(nlev - 1):
+            prefixes.append(p)
+            p = p + "1.submodule.1."
+        tape = self.tape
+        atts = []          # (att tensor, backward) in hook order: coarsest first
+        # ---- encoder
+        for l in range(nlev - 1):
+            pr = prefixes[l]
+            if l == 0:
+                bw = self.residual_unit(pr + "0.", None, None, cat[0], 0, ch[0], ks[0], 2, cin1=xv)
+            else:
+                bw = self.residual_unit(pr + "0.", dn[l - 1].view(), gdn[l - 1], cat[l], 0, ch[l], ks[l], 2)
+            tape.append((bw, lambda l=l: gcat[l].buf.view(0, ch[l])))
+            bwd = self.convolution(pr + "1.submodule.0.", cat[l].view(0, ch[l]), gcat[l], dn[l].view(), sks[l], strides[l],
+                                   c0=0, Cx=ch[l])
+            tape.append((bwd, lambda l=l: gdn[l].buf.view()))
+        # ---- bottom
+        pb = prefixes[-1] + "1.submodule.1."
+        kb = ks[-1]
+        bot = self._buf(ch[-1], dims[-1])
+        gbot = _GradBuf(bot)
+        if att_on:
+            gbuf, gg, att, bwa = self.attention(pb + "0.", dn[-1], gdn[-1], kb)
+            atts.append((att, bwa))
+            bwr = self.residual_unit(pb + "1.", gbuf.view(), gg, bot, 0, ch[-1], kb, 2)
+            tape.append((bwa, None))
+            tape.append((bwr, lambda: gbot.buf.view()))
+        else:
+            bwr = self.residual_unit(pb, dn[-1].view(), gdn[-1], bot, 0, ch[-1], kb, 2)
+            tape.append((bwr, lambda: gbot.buf.view()))
+        # ---- decoder
+        sub, gsub = bot, gbot
+        logits = None
+        for l in range(nlev - 2, -1, -1):
+            pr = prefixes[l]
+            bwu = self.convolution(pr + "1.submodule.2.", sub.view(), gsub, cat[l].view(ch[l], ch[l]), sks[l], strides[l],
+                                   transposed=True)
+            tape.append((bwu, lambda l=l: gcat[l].buf.view(ch[l], ch[l])))
+            pu = pr + "2."
+            src_buf, src_g = cat[l], gcat[l]
+            if att_on:
+                gbuf, gg, att, bwa = self.attention(pu + "0.", cat[l], gcat[l], ks[l])
+                atts.append((att, bwa))
+                tape.append((bwa, None))
+                src_buf, src_g = gbuf, gg
+                pu = pu + "1."
+            if l > 0:
+                out = self._buf(ch[l], dims[l])   # the decoder ResidualUnit at level l maps 2*ch[l] -> ch[l]
+                gout = _GradBuf(out)
+                bwr = self.residual_unit(pu, src_buf.view(), src_g, out, 0, ch[l], ks[l], 1)
+                tape.append((bwr, lambda gout=gout: gout.buf.view()))
+                sub, gsub = out, gout
+            else:
+                # top unit: conv_only + 1x1x1 shortcut, both linear: one small-Cout conv with the shortcut folded
+                # into the centre tap; the parameter gradients are un-folded in backward
+                k0 = ks[0]
+                nout = m.out_channels
+                wc, bc = self.p[pu + "conv.unit0.conv.weight"], self.p[pu + "conv.unit0.conv.bias"]
+                wr, br = self.p[pu + "residual.weight"], self.p[pu + "residual.bias"]
+                wf = wc.detach().float().clone()
+                wf[:, :, k0[0] // 2, k0[1] // 2, k0[2] // 2] += wr.detach().reshape(nout, -1).float()
+                wg = pack_conv_weight(wf, False)                       # [taps][Cin][nout]
+                bf = (bc.detach() + br.detach()).float().contiguous()
+                logits = torch.empty((self.B, nout) + dims[0], device=self.dev)
+                lv = f32view(logits)
+                g0 = self._geom(k0)
+                sv = src_buf.view()
+                self._chk(lib.vsseg_conv3d_smallcout(C.byref(sv), C.byref(lv), C.byref(g0), wg.data_ptr(), bf.data_ptr(), 0, 1.0,
+                                                     None, s), "logits")
+                self.keep += [wg, bf, sv, lv]
+
+                def bw_top(dlogits, sv=sv, src_g=src_g, wg=wg, g0=g0, k0=k0, pu=pu, nout=nout, wc=wc):
+                    dl = dlogits.float().contiguous()
+                    dlv = f32view(dl)
+                    taps = k0[0] * k0[1] * k0[2]
+                    dw = torch.zeros((taps, sv.C, nout), device=self.dev)
+                    db = torch.zeros(nout, device=self.dev)
+                    dx = src_g.buf.view()
+                    if src_g.filled:
+                        raise RuntimeError("top unit must be the first writer of its input gradient")
+                    self._chk(lib.vsseg_conv3d_smallcout_bwd(C.byref(sv), C.byref(dlv), None, C.byref(g0), wg.data_ptr(), 0,
+                                                             C.byref(dx), dw.data_ptr(), db.data_ptr(), s), "logits_bwd")
+                    src_g.filled = True
+                    cin = wc.shape[1]
+                    dwt = dw[:, :cin, :].reshape(k0[0], k0[1], k0[2], cin, nout).permute(4, 3, 0, 1, 2)
+                    self._addgrad(pu + "conv.unit0.conv.weight", dwt)
+                    self._addgrad(pu + "residual.weight", dwt[:, :, k0[0] // 2, k0[1] // 2, k0[2] // 2].reshape(nout, cin, 1, 1, 1))
+                    self._addgrad(pu + "conv.unit0.conv.bias", db)
+                    self._addgrad(pu + "residual.bias", db)
+                    self.keep += [dl, dw, db]
+
+                self.bw_top = bw_top
+        self.atts = atts
+        return logits, [a for a, _ in atts]
+
+    def backward(self, dlogits, datts):
+        """Runs the tape in reverse; returns {parameter name: gradient}."""
+        att_grads = {}
+        for (att, bwa), g in zip(self.atts, datts):
+            att_grads[id(bwa)] = g
+        self.bw_top(dlogits)
+        for bw, grad_view in reversed(self.tape):
+            if grad_view is None:
+                bw(att_grads.get(id(bw)))
+            else:
+                bw(grad_view())
+        return self.pgrads
+
+
+def _pad_cin(w, transposed, c):
+    d = 0 if transposed else 1
+    if w.shape[d] == c:
+        return w
+    pad = [0, 0] * (w.dim() - 1 - d) + [0, c - w.shape[d]]
+    return torch.nn.functional.pad(w, pad)
+
+
+def _pad_cout(w, transposed, c):
+    d = 1 if transposed else 0
+    if w.shape[d] == c:
+        return w
+    pad = [0, 0] * (w.dim() - 1 - d) + [0, c - w.shape[d]]
+    return torch.nn.functional.pad(w, pad)
+
+
+class _UNetTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, names, *params):
+        step = UNetTrainStep(model, x)
+        logits, atts = step.forward(x)
+        ctx.step, ctx.names = step, names
+        return (logits, *atts)
+
+    @staticmethod
+    def backward(ctx, dlogits, *datts):
+        step = ctx.step
+        if dlogits is None:
+            raise RuntimeError("the logits received no gradient")
+        grads = step.backward(dlogits, list(datts))
+        out = [grads.get(n) for n in ctx.names]
+        ctx.step = None
+        return (None, None, None, *out)
 
 
 def unet_train_forward(model, x):
-    raise NotImplementedError(
-        "train-mode forward of UNet2d5_spvPA on CUDA needs the native backward kernels, which are not "
-        "built yet; there is deliberately no eager-torch CUDA fallback (use model.eval() for inference)")
+    """Train-mode forward of UNet2d5_spvPA on CUDA through the native kernels; differentiable w.r.t. every
+    parameter of `model` (BatchNorm running statistics are updated in place)."""
+    if not x.is_cuda:
+        raise _lib.NativeLibraryError("unet_train_forward needs a CUDA tensor (no CPU fallback)")
+    if not model._plan_supported():
+        raise NotImplementedError("the native training path covers the reference configuration "
+                                  "(3-D, num_res_units=2, BatchNorm, PReLU, 1 input channel)")
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    names = tuple(n for n, _ in named)
+    outs = _UNetTrainFn.apply(model, x, names, *[p for _, p in named])
+    return outs[0], list(outs[1:])
