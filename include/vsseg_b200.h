@@ -220,6 +220,12 @@ int vsseg_act_bwd(const vsseg_act8* y, const vsseg_act8* dy, float slope, const 
 int vsseg_act8_add(const vsseg_act8* a, const vsseg_act8* b, const vsseg_act8* out, void* stream);
 int vsseg_conv3d_wgrad(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_conv_geom* g, float* dw,
                        int32_t cout_pad, float* dbias, void* stream);
+/* Tensor-core weight gradient (tcgen05, MN-major operands read straight from the act8 z lines, bf16x3, split-K with
+ * fp32 atomics) for stride-1 convs whose z extent is a multiple of 128, Cin % 16 == 0, Cout <= 128; dw as
+ * vsseg_conv3d_wgrad (zeroed by the caller).  The bias gradient is vsseg_bn_stats(dc) (its plain sums). */
+int vsseg_conv3d_wgrad_tc_supported(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_conv_geom* g);
+int vsseg_conv3d_wgrad_tc(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_conv_geom* g, float* dw,
+                          int32_t cout_pad, void* stream);
 int vsseg_conv3d_cin1_wgrad(const vsseg_f32view* src, const vsseg_act8* dc, const vsseg_conv_geom* g,
                             float* dw, float* dbias, void* stream);
 int vsseg_conv3d_smallcout_bwd(const vsseg_act8* x, const vsseg_f32view* dy, const vsseg_f32view* y,

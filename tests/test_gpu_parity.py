@@ -390,3 +390,43 @@ def test_unet_train_step_matches_torch_autograd(attention, shape):
     br, bn = dict(ref.named_buffers()), dict(nat.named_buffers())
     for name, b in br.items():
         assert (bn[name].cpu().float() - b.float()).abs().max().item() < 1e-4 * max(1.0, b.float().abs().max().item()), name
+
+
+@pytest.mark.parametrize("B,cin,cout,dims,k", [
+    (1, 16, 16, (4, 6, 128), (3, 3, 1)), (2, 32, 48, (3, 4, 128), (3, 3, 3)), (1, 96, 48, (2, 3, 128), (3, 3, 3)),
+    (1, 64, 32, (4, 4, 256), (3, 3, 1)), (1, 16, 32, (4, 4, 128), (1, 1, 1)), (1, 48, 40, (3, 3, 128), (3, 3, 3)),
+])
+def test_tcgen05_wgrad_matches_torch(B, cin, cout, dims, k):
+    """Tensor-core weight gradient (MN-major operands, split-K atomics) vs torch.nn.grad on the CPU, and vs the
+    CUDA-core reduction kernel it replaces."""
+    import ctypes as C
+    from vs_seg_b200 import lib as vlib
+    from vs_seg_b200.tensors import Act8Buffer
+    dev = _dev()
+    lib = vlib.load()
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn((B, cin) + dims, generator=g)
+    dy = torch.randn((B, cout) + dims, generator=g)
+    pad = tuple((kk - 1) // 2 for kk in k)
+    ref = torch.nn.grad.conv3d_weight(x.double(), (cout, cin) + k, dy.double(), padding=pad)      # [cout, cin, k]
+    cpad = (cout + 15) // 16 * 16
+    c8 = (cout + 7) // 8 * 8
+    xb = Act8Buffer(B, cin, *dims, dev).from_ncdhw(x.to(dev))
+    db = Act8Buffer(B, c8, *dims, dev).from_ncdhw(torch.nn.functional.pad(dy, (0, 0, 0, 0, 0, 0, 0, c8 - cout)).to(dev))
+    geom = vlib.ConvGeom(*k, 1, 1, 1, 0)
+    xv, dv = xb.view(), db.view()
+    assert lib.vsseg_conv3d_wgrad_tc_supported(C.byref(xv), C.byref(dv), C.byref(geom)) == 1
+    taps = k[0] * k[1] * k[2]
+    s = torch.cuda.current_stream(dev).cuda_stream
+    outs = []
+    for tc in (True, False):
+        dw = torch.zeros((taps, cin, cpad), device=dev)
+        if tc:
+            vlib.check(lib.vsseg_conv3d_wgrad_tc(C.byref(xv), C.byref(dv), C.byref(geom), dw.data_ptr(), cpad, s), "wgrad_tc")
+        else:
+            dbias = torch.zeros(cpad, device=dev)
+            vlib.check(lib.vsseg_conv3d_wgrad(C.byref(xv), C.byref(dv), C.byref(geom), dw.data_ptr(), cpad, dbias.data_ptr(), s),
+                       "wgrad")
+        got = dw[:, :, :cout].reshape(*k, cin, cout).permute(4, 3, 0, 1, 2).cpu().double()
+        outs.append(got)
+        assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item(), ("tc" if tc else "cuda-core")

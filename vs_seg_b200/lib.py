@@ -76,6 +76,8 @@ _SIGNATURES = {
     "vsseg_act_bwd": (C.c_int, [_P(Act8), _P(Act8), C.c_float, _P(Act8), C.c_void_p]),
     "vsseg_act8_add": (C.c_int, [_P(Act8), _P(Act8), _P(Act8), C.c_void_p]),
     "vsseg_conv3d_wgrad": (C.c_int, [_P(Act8), _P(Act8), _P(ConvGeom), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsseg_conv3d_wgrad_tc_supported": (C.c_int, [_P(Act8), _P(Act8), _P(ConvGeom)]),
+    "vsseg_conv3d_wgrad_tc": (C.c_int, [_P(Act8), _P(Act8), _P(ConvGeom), C.c_void_p, C.c_int32, C.c_void_p]),
     "vsseg_conv3d_cin1_wgrad": (C.c_int, [_P(F32View), _P(Act8), _P(ConvGeom), C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsseg_conv3d_smallcout_bwd": (C.c_int, [_P(Act8), _P(F32View), _P(F32View), _P(ConvGeom), C.c_void_p, C.c_int32,
                                              _P(Act8), C.c_void_p, C.c_void_p, C.c_void_p]),

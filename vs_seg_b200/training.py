@@ -27,6 +27,11 @@ from .tensors import Act8Buffer, f32view
 _BN_EPS, _BN_MOM = 1e-5, 0.1
 
 
+def _lib_tc_wgrad():
+    import os
+    return os.environ.get("VSSEG_TC_WGRAD", "1") != "0"
+
+
 class _GradBuf:
     """Gradient of an activation tensor: first writer stores, later writers accumulate."""
 
@@ -124,8 +129,16 @@ class UNetTrainStep:
         dw = torch.zeros((taps, x.C, cpad), device=self.dev)
         db = torch.zeros(cpad, device=self.dev)
         g = self._geom(k, stride, transposed)
-        self._chk(self.lib.vsseg_conv3d_wgrad(C.byref(x), C.byref(dc), C.byref(g), dw.data_ptr(), cpad, db.data_ptr(),
-                                              self.stream), "conv3d_wgrad")
+        if _lib_tc_wgrad() and self.lib.vsseg_conv3d_wgrad_tc_supported(C.byref(x), C.byref(dc), C.byref(g)):
+            # tensor-core weight gradient; the bias gradient is the plain channel sum of dc
+            self._chk(self.lib.vsseg_conv3d_wgrad_tc(C.byref(x), C.byref(dc), C.byref(g), dw.data_ptr(), cpad, self.stream),
+                      "conv3d_wgrad_tc")
+            sums = torch.zeros(2 * dc.C, dtype=torch.float64, device=self.dev)
+            self._chk(self.lib.vsseg_bn_stats(C.byref(dc), sums.data_ptr(), self.stream), "bn_stats")
+            db[:dc.C] = sums[:dc.C].float()
+        else:
+            self._chk(self.lib.vsseg_conv3d_wgrad(C.byref(x), C.byref(dc), C.byref(g), dw.data_ptr(), cpad, db.data_ptr(),
+                                                  self.stream), "conv3d_wgrad")
         dw = dw[:, :cin, :cout].reshape(k[0], k[1], k[2], cin, cout)
         self._addgrad(wname, dw.permute(3, 4, 0, 1, 2) if transposed else dw.permute(4, 3, 0, 1, 2))
         self._addgrad(bname, db[:cout])
