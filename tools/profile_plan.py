@@ -41,5 +41,33 @@ def main():
     print("\n".join(lines))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "--host"):
     main()
+
+
+def host_cost():
+    """Host-side cost of issuing one patch (no device sync inside the loop)."""
+    import time
+    dev = torch.device("cuda:0")
+    net, _ = bench.build_net(dev)
+    plan = net.eval_plan(bench.ROI, 1, dev)
+    vol = torch.randn((1, 1) + bench.VOLUME, device=dev)
+    acc = torch.zeros((1, 2) + bench.VOLUME, device=dev)
+    imap = sw.importance_map(bench.ROI, "gaussian", 0.125, dev)
+    a, b = f32view(vol, (0, 0, 0), bench.ROI), f32view(acc, (0, 0, 0), bench.ROI)
+    for _ in range(3):
+        plan.run(a, b, imap.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 20
+    for _ in range(n):
+        plan.run(a, b, imap.data_ptr())
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"host issue time per patch {1e3 * (t1 - t0) / n:.3f} ms; wall incl. drain {1e3 * (t2 - t0) / n:.3f} ms; "
+          f"{len(plan.steps)} launches")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--host":
+    host_cost()

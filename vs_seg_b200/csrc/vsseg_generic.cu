@@ -228,37 +228,53 @@ struct Cin1Args {
 
 template <int COUT>
 __global__ void __launch_bounds__(128) conv_cin1_kernel(const Cin1Args a) {
-    __shared__ float ws[27 * COUT];
+    // block = one (b, x, y) line segment of 128 z; all per-voxel index arithmetic is 32-bit and block-uniform
+    // (the first version spent ~1000 instructions per voxel, most of them 64-bit div/mod: instruction-bound)
+    __shared__ float4 ws4[27 * COUT / 4];
+    float* ws = reinterpret_cast<float*>(ws4);
     const int taps = a.g.kx * a.g.ky * a.g.kz;
     for (int i = threadIdx.x; i < taps * COUT; i += blockDim.x) ws[i] = a.w[i];
     __syncthreads();
     const int X = a.out.X, Y = a.out.Y, Z = a.out.Z;
-    const int64_t nvox = (int64_t)a.out.B * X * Y * Z;
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nvox) return;
-    const int z = (int)(v % Z), y = (int)((v / Z) % Y), x = (int)((v / ((int64_t)Z * Y)) % X);
-    const int b = (int)(v / ((int64_t)Z * Y * X));
+    const int nzt = (Z + 127) / 128;
+    int t = blockIdx.x;
+    const int zt = t % nzt; t /= nzt;
+    const int y = t % Y; t /= Y;
+    const int x = t % X;
+    const int b = t / X;
+    const int z = zt * 128 + threadIdx.x;
+    if (z >= Z) return;
     const int px = (a.g.kx - 1) / 2, py = (a.g.ky - 1) / 2, pz = (a.g.kz - 1) / 2;
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    const float* src = a.in.ptr + (int64_t)b * a.in.sb;
     int tap = 0;
     for (int tx = 0; tx < a.g.kx; ++tx)
-        for (int ty = 0; ty < a.g.ky; ++ty)
+        for (int ty = 0; ty < a.g.ky; ++ty) {
+            const int xi = x - px + tx, yi = y - py + ty;
+            const bool line_in = xi >= 0 && xi < X && yi >= 0 && yi < Y;      // block-uniform
+            const float* lp = src + (int64_t)xi * a.in.sx + (int64_t)yi * a.in.sy;
             for (int tz = 0; tz < a.g.kz; ++tz, ++tap) {
-                int xi = x - px + tx, yi = y - py + ty, zi = z - pz + tz;
-                if (xi < 0 || xi >= X || yi < 0 || yi >= Y || zi < 0 || zi >= Z) continue;
-                float s = __ldg(a.in.ptr + b * a.in.sb + xi * a.in.sx + yi * a.in.sy + zi * a.in.sz);
+                const int zi = z - pz + tz;
+                const float sv = (line_in && zi >= 0 && zi < Z) ? __ldg(lp + (int64_t)zi * a.in.sz) : 0.f;
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(s, ws[tap * COUT + c], acc[c]);
+                for (int q = 0; q < COUT / 4; ++q) {
+                    const float4 w = ws4[tap * (COUT / 4) + q];
+                    acc[4 * q] = fmaf(sv, w.x, acc[4 * q]);
+                    acc[4 * q + 1] = fmaf(sv, w.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(sv, w.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(sv, w.w, acc[4 * q + 3]);
+                }
             }
+        }
     __nv_bfloat16* out_hi = (__nv_bfloat16*)a.out.hi;
 #pragma unroll
     for (int g8 = 0; g8 < COUT / 8; ++g8) {
         float o[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            int cc = g8 * 8 + c;
+            const int cc = g8 * 8 + c;
             o[c] = apply_act(acc[cc] * __ldg(a.ep.scale + cc) + __ldg(a.ep.shift + cc), a.ep.act, a.ep.slope);
         }
         uint4 h, l;
@@ -529,7 +545,8 @@ int vsseg_conv3d_cin1(const vsseg_f32view* in, const vsseg_act8* out, const vsse
     VSSEG_REQUIRE(w && ep && ep->scale && ep->shift, "conv3d_cin1: NULL weights/epilogue");
     Cin1Args a{*in, *out, *g, w, *ep};
     const int64_t nvox = (int64_t)out->B * out->X * out->Y * out->Z;
-    conv_cin1_kernel<16><<<(unsigned)((nvox + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    const unsigned nblk = (unsigned)((int64_t)out->B * out->X * out->Y * ((out->Z + 127) / 128));
+    conv_cin1_kernel<16><<<nblk, 128, 0, (cudaStream_t)stream>>>(a);
     return check_launch("conv3d_cin1");
 }
 
