@@ -20,6 +20,9 @@
 // (+ residual / + shortcut accumulator) -> split-bf16 -> global (act8).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <vector>
 
 #include "vsseg_ptx.cuh"
 
@@ -32,6 +35,12 @@ struct TcOp {        // one tcgen05.mma: D[128 x n8*8 columns at col] += A[128 x
     uint16_t col;    // first TMEM column written
     uint16_t n8;     // N / 8 of this instruction (several adjacent accumulators share one A read)
 };
+// The MMA-issuing warp shares its scheduler with four ALU-busy epilogue warps, so every instruction it
+// needs per MMA costs issue slots it only gets a fraction of (tools/ubench/mma_ctx.cu: 45 -> 110-160
+// cycles per N=48 MMA next to busy warps; measured ~75-100 in this kernel with 15 instructions per MMA).
+// The device therefore reads one ready-made 16-byte record per merged product and derives the three
+// bf16x3 passes from it with two adds: ~4 uniform instructions per MMA.
+struct __align__(16) TcEl { uint32_t a_lo, b_lo, col, idesc; };   // one merged product = 3 MMAs (hi*hi, lo*hi, hi*lo)
 struct TcBox {       // one TMA box of a stage (issued for the hi and the lo plane)
     uint16_t dst16;  // offset inside the hi-plane A region, 16 B units
     int8_t dy, dz;   // input-coordinate shift of the box origin
@@ -40,6 +49,7 @@ struct TcAcc {       // where an accumulator lands in the output
     int16_t y_add;   // output y of M-tile line 0, relative to the tile's output y base
     int8_t z_add;    // output z phase
     int8_t yl;       // M-grid line offset of the accumulator's line group (for the partial-group mask)
+    int32_t off8;    // (y_add * Zout + z_add) * 8: element offset of the accumulator inside an act8 channel group
 };
 
 constexpr int TC_MAX_OPS = 144;
@@ -66,7 +76,7 @@ struct TcArgs {
     uint32_t lbo_a, lbo_b, lbo_b2, idesc, tmem_cols;
     // tile decomposition of the M grid
     int ntz, nty, ntx, nsel, npx, nsplit, ntiles, nbuf;
-    int XT, npl;             // x rows per tile; stages per chunk (x planes XT+2 when XT > 1, else x taps nj)
+    int XT, Xm;              // x rows per tile (the CTA marches along them), x extent of the M grid
     int LZ, LY, YL, Ym;      // M-tile shape, y lines of the M grid per CTA tile, y extent of the M grid
     int n_cta;               // output channels per CTA (multiple of 16), n_real: channels to store
     int cout;                // real Cout (multiple of 8)
@@ -83,20 +93,44 @@ struct TcArgs {
     vsseg_f32view outf;
     const float* sw_weight;
     vsseg_act8 in, in2;
-    TcOp ops[TC_MAX_OPS];
+    unsigned long long* dbg;  // VSSEG_TC_DEBUG: per-CTA cycle counters [gridDim.x][8]
+    int dbgf;                 // VSSEG_TC_DBGF experiments (timing only, results invalid): 1 no epilogue work, 2 no copies
+    TcOp ops[TC_MAX_OPS];      // host-side description (plan dump)
     TcOp ops2[TC_MAX_OPS2];
     TcBox boxes[TC_MAX_BOX];
     TcAcc accs[TC_MAX_ACC];
+    TcEl el[TC_MAX_OPS / 3];   // what the MMA thread reads
+    TcEl el2[TC_MAX_OPS2 / 3];
+    uint32_t desc_hi;          // upper descriptor word (SBO = 128 B, version 1)
+    int partial;               // the last y line group is partial (rows beyond Ym are masked)
 };
 
 constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
-constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each draining every other accumulator
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0: producer, warp 1: MMA issuer + TMEM owner, rest: epilogue
+#ifndef VSSEG_TC_EPI_WARPS
+#define VSSEG_TC_EPI_WARPS 16
+#endif
+#ifndef VSSEG_TC_MMA_WARPS
+#define VSSEG_TC_MMA_WARPS 3
+#endif
+constexpr int TC_EPI_WARPS = VSSEG_TC_EPI_WARPS;  // four warps per TMEM lane quadrant, each draining every fourth (accumulator, 16-column) unit
+// MMA issue is the bottleneck of the narrow layers: one thread sustains one MMA per ~60 cycles (5 uniform
+// instructions each, slower next to ALU-busy epilogue warps; tools/ubench/mma_issue.cu, mma_ctx.cu) while an
+// N=48 MMA executes in 44.  Three issuing warps therefore own the output ROWS round-robin (row g -> issuer
+// g % 3): a plane of the x march feeds three consecutive rows, i.e. one per issuer, and every TMEM
+// accumulator is only ever written by one thread (MMAs of different threads into the SAME columns are
+// not ordered - splitting one stage's products over warps gave sporadic lost updates).  Completion is
+// tracked by one commit per issuer on every barrier.
+constexpr int TC_MMA_WARPS = VSSEG_TC_MMA_WARPS;
+constexpr int TC_EPI_WARP0 = 1 + TC_MMA_WARPS;   // first epilogue warp (a multiple of 4 plus 1: quadrant = warp % 4)
+constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);  // warp 0: producer, warps 1-4: MMA issuers (warp 1 owns TMEM), rest: epilogue
+constexpr int TC_MAX_SLOT = 8;    // accumulator row slots in TMEM
 
 __device__ uint4 g_zero_line[136];  // source of padding lines / halo rows for the bulk-copy producer (zero-initialised)
 
 struct TcTile {
-    int sel, tz, ty, mx, b, px, ns, my0, mz0, njx;
+    int sel, tz, ty, mx, b, px, ns, my0, mz0;
+    int xt;          // x rows of this tile (the last x segment may be shorter)
+    int q_lo, q_hi;  // first / last staged x plane that lies inside the volume
 };
 __device__ __forceinline__ TcTile decode_tile(const TcArgs& a, int t) {
     TcTile T;
@@ -107,39 +141,185 @@ __device__ __forceinline__ TcTile decode_tile(const TcArgs& a, int t) {
     T.b = t;
     T.px = T.sel / a.nsplit; T.ns = T.sel % a.nsplit;
     T.my0 = T.ty * a.YL; T.mz0 = T.tz * a.LZ;
-    T.njx = (a.npx == 2 && T.px == 0) ? 1 : a.npl;  // transposed conv, even x phase: only the centre x tap
+    T.xt = min(a.XT, a.Xm - T.mx);
+    // plane q holds input x = mx*sx + q + xoff and feeds row r = q - dx through x tap dx.
+    // transposed conv, even x phase: only the centre x tap (plane 0)
+    const int qlim = (a.npx == 2 && T.px == 0) ? 1 : T.xt + a.nj - 1;
+    const int x0 = T.mx * a.sx + a.xoff;
+    T.q_lo = max(0, -x0);
+    T.q_hi = min(qlim - 1, a.Xin - 1 - x0);
     return T;
 }
 
-// Persistent kernel: CTA i walks tiles i, i+gridDim.x, ...  The shared-memory ring runs across tile
-// boundaries (the producer prefetches the next tile during the MMAs/epilogue of the current one) and
-// the accumulators are double-buffered in TMEM when two tiles fit (nbuf = 2), so the epilogue of tile
-// k overlaps the main loop of tile k+1.
+struct EpiCtx {
+    const TcArgs& a;
+    const float* ep_c;
+    uint32_t tacc, row_cols;
+    int64_t row_off, cgs, lo_out, lo_res;
+    __nv_bfloat16* out_b;
+    const __nv_bfloat16* res_b;
+    int b, ox, my0, mz0, ly, zz, co0, nreal;
+    bool sc, sig;
+    float slope;
+};
+template <bool SC, int RM>
+struct EpiUnit {
+    int ai, c;
+    uint32_t v[16], v2[SC ? 16 : 1];
+    uint4 rh[RM == 1 ? 2 : 1], rl[RM == 1 ? 2 : 1];
+    float rsrc;
+    int oy, oz;
+    bool live, valid;
+};
+
+// issue the TMEM loads of one unit and fetch its residual operands (they arrive while the loads are in flight)
+template <int OM, bool SC, int RM>
+__device__ __forceinline__ void epi_load(const EpiCtx& X, EpiUnit<SC, RM>& U) {
+    const TcArgs& a = X.a;
+    const int c0 = U.c << 4;
+    U.live = c0 < X.nreal;   // padding columns of the Cout slice (warp-uniform)
+    if (!U.live) return;
+    const uint32_t taddr = X.tacc + (uint32_t)(U.ai * a.n_cta + c0);
+    tmem_ld16(taddr, U.v);
+    if constexpr (SC) tmem_ld16(taddr + X.row_cols, U.v2);
+    // rows of a partial (zero-padded) line group load their TMEM lane like everyone else
+    // (tcgen05.ld is warp-collective) but neither read the residual nor store
+    U.valid = !a.partial || X.my0 + X.ly + a.accs[U.ai].yl < a.Ym;
+    U.rsrc = 0.f;
+    U.oy = U.oz = 0;
+    if constexpr (RM == 2 || OM == 1) {
+        U.oy = (X.my0 + X.ly) * a.uy + a.accs[U.ai].y_add;
+        U.oz = (X.mz0 + X.zz) * a.uz + a.accs[U.ai].z_add;
+    }
+    if constexpr (RM == 1) {
+      if (U.valid) {
+        const __nv_bfloat16* rp = X.res_b + X.row_off + a.accs[U.ai].off8 + (int64_t)(U.c * 2) * X.cgs;
+        U.rh[0] = ldg128(rp);
+        U.rl[0] = ldg128(rp + X.lo_res);
+        if (X.nreal - c0 > 8) {
+            U.rh[1] = ldg128(rp + X.cgs);
+            U.rl[1] = ldg128(rp + X.cgs + X.lo_res);
+        }
+      }
+    } else if constexpr (RM == 2) {
+        if (U.valid) U.rsrc = __ldg(a.rsrc.ptr + X.b * a.rsrc.sb + X.ox * a.rsrc.sx + U.oy * a.rsrc.sy + U.oz * a.rsrc.sz);
+    }
+}
+
+// BN scale/shift -> PReLU/ReLU/sigmoid -> (+ shortcut accumulator | + residual) -> split-bf16 -> global
+template <int OM, bool SC, int RM>
+__device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) {
+    const TcArgs& a = X.a;
+    if (!U.live || !U.valid || (a.dbgf & 1)) return;
+    const int c0 = U.c << 4;
+    const float* ep_c = X.ep_c;
+    if constexpr (OM == 1) {
+        // planar fp32 output: attention map (sigmoid) or logits, optionally blended into the
+        // sliding-window accumulator (MONAI sliding_window_inference step 6)
+        const int Yo = a.out.Y, Zo = a.out.Z;
+        const float sw = a.sw_weight ? __ldg(a.sw_weight + ((int64_t)X.ox * Yo + U.oy) * Zo + U.oz) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {   // Cout <= 2 on this path (static indices keep v[] in registers)
+            if (q >= a.cout) break;
+            float f = __uint_as_float(U.v[q]) * ep_c[q] + ep_c[256 + q];
+            f = apply_act(f, a.ep.act, X.slope);
+            float* o = a.outf.ptr + X.b * a.outf.sb + q * a.outf.sc + X.ox * a.outf.sx + U.oy * a.outf.sy + U.oz * a.outf.sz;
+            if (a.sw_weight) *o += sw * f;
+            else *o = f;
+        }
+        return;
+    } else {
+    const int ngrp = min(2, (X.nreal - c0 + 7) >> 3);
+    __nv_bfloat16* op = X.out_b + X.row_off + a.accs[U.ai].off8 + (int64_t)(U.c * 2) * X.cgs;
+    const float* e = ep_c + X.co0 + c0;
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+        if (g8 >= ngrp) break;
+        float scl[8], sft[8], o[8];
+        *reinterpret_cast<float4*>(scl) = *reinterpret_cast<const float4*>(e + g8 * 8);
+        *reinterpret_cast<float4*>(scl + 4) = *reinterpret_cast<const float4*>(e + g8 * 8 + 4);
+        *reinterpret_cast<float4*>(sft) = *reinterpret_cast<const float4*>(e + g8 * 8 + 256);
+        *reinterpret_cast<float4*>(sft + 4) = *reinterpret_cast<const float4*>(e + g8 * 8 + 260);
+        if (X.sig) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float f = fmaf(__uint_as_float(U.v[g8 * 8 + q]), scl[q], sft[q]);
+                o[q] = 1.0f / (1.0f + expf(-f));
+            }
+        } else {
+            // PReLU / ReLU / identity: f + (slope - 1) * min(f, 0)
+            const float sm1 = X.slope - 1.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float f = fmaf(__uint_as_float(U.v[g8 * 8 + q]), scl[q], sft[q]);
+                o[q] = fmaf(fminf(f, 0.f), sm1, f);
+            }
+        }
+        if constexpr (SC || RM == 2) {
+            float post[8];
+            *reinterpret_cast<float4*>(post) = *reinterpret_cast<const float4*>(e + g8 * 8 + 512);
+            *reinterpret_cast<float4*>(post + 4) = *reinterpret_cast<const float4*>(e + g8 * 8 + 516);
+            if constexpr (SC) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] += __uint_as_float(U.v2[g8 * 8 + q]) + post[q];
+            } else {
+                float rw[8];
+                *reinterpret_cast<float4*>(rw) = *reinterpret_cast<const float4*>(e + g8 * 8 + 768);
+                *reinterpret_cast<float4*>(rw + 4) = *reinterpret_cast<const float4*>(e + g8 * 8 + 772);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] += fmaf(rw[q], U.rsrc, post[q]);
+            }
+        }
+        if constexpr (RM == 1) {
+            float rr[8];
+            unpack8(U.rh[g8], U.rl[g8], rr);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] += rr[q];
+        }
+        uint4 h, l;
+        pack8(o, h, l);
+        __nv_bfloat16* p = op + g8 * X.cgs;
+        *reinterpret_cast<uint4*>(p) = h;
+        *reinterpret_cast<uint4*>(p + X.lo_out) = l;
+    }
+    }
+}
+
+// Persistent kernel: CTA i walks tiles i, i+gridDim.x, ...  A tile is XT consecutive x rows of one
+// (y line group, z tile, Cout slice).  The CTA marches along x: every input plane is staged ONCE per
+// 16-channel chunk and feeds the (up to) three output rows that use it through the three x taps, so
+// the L2->shared traffic per output row is (XT+2)/XT planes instead of 3.  Output rows live in R
+// TMEM "row slots" used round-robin: a row is complete after the plane behind it, its slot is drained
+// by the epilogue warps while the MMA thread works on the following planes, then re-zeroed and handed
+// back.  The shared-memory ring runs across row and tile boundaries.  XT = 1 is the plain
+// one-row-per-tile schedule (strided / transposed convs, layers whose accumulators fill TMEM).
+template <int OM, bool SC, int RM>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ CUtensorMap tmap2,
                                                              const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [nstage]
     uint64_t* empty = full + 8;                          // [nstage]
-    uint64_t* acc_full = full + 16;                      // [2]
-    uint64_t* acc_empty = full + 18;                     // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 20);
+    uint64_t* acc_full = full + 16;                      // [nslot]
+    uint64_t* acc_empty = full + 24;                     // [nslot]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 32);
     // per-channel epilogue constants of this CTA's Cout slice(s), staged once: [scale | shift | bias2 | res_w | res_b][256]
     float* ep_c = reinterpret_cast<float*>(smem + 1024);
     const uint32_t ring = smem_u32(smem) + TC_HDR;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nmain = a.nchunk * a.npl, ntot = nmain + a.nchunk2 * a.XT;
     const uint32_t row_cols = (uint32_t)(a.nacc * a.n_cta);
-    const uint32_t buf_cols = (uint32_t)a.XT * row_cols * (a.nchunk2 ? 2 : 1);
+    const uint32_t slot_cols = row_cols * (a.nchunk2 ? 2 : 1);
+    const int R = a.nbuf;
+    const int njm1 = a.nj - 1, jc = a.nj >> 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.nstage; ++i) {
             mbar_init(full + i, 1);
-            mbar_init(empty + i, 1);
+            mbar_init(empty + i, TC_MMA_WARPS);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(acc_full + i, 1);
+        for (int i = 0; i < TC_MAX_SLOT; ++i) {
+            mbar_init(acc_full + i, TC_MMA_WARPS);
             mbar_init(acc_empty + i, TC_EPI_WARPS);
         }
         fence_barrier_init();
@@ -154,9 +334,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         for (int i = threadIdx.x; i < ncp; i += TC_THREADS) {
             ep_c[i] = a.ep.scale[i];
             ep_c[256 + i] = a.ep.shift[i];
-            ep_c[512 + i] = a.nchunk2 ? a.bias2[i] : 0.f;
+            ep_c[512 + i] = a.nchunk2 ? a.bias2[i] : (a.res_mode == 2 ? a.res_b[i] : 0.f);   // added after the activation
             ep_c[768 + i] = a.res_mode == 2 ? a.res_w[i] : 0.f;
-            ep_c[1024 + i] = a.res_mode == 2 ? a.res_b[i] : 0.f;
         }
     }
     if (a.line_mode && a.hz > 0) {
@@ -175,257 +354,279 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     if (warp == 0 && a.line_mode) {
         // ===== bulk-copy producer: every lane issues whole z lines (2 KB contiguous in act8) =====
         int it = 0;
+        long long t_wait = 0, t_beg = clock64();
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const TcTile T = decode_tile(a, tile);
-            for (int s = 0; s < ntot; ++s) {
-                const bool seg2 = s >= nmain;
-                const int c = seg2 ? (s - nmain) / a.XT : s / a.npl, j = seg2 ? 0 : s % a.npl;
-                const int x = seg2 ? T.mx + (s - nmain) % a.XT : T.mx * a.sx + j + a.xoff;
-                if (x < 0 || x >= a.Xin || j >= T.njx) continue;
-                const int st = it % a.nstage;
-                mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
-                const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-                const vsseg_act8& src = seg2 ? a.in2 : a.in;
-                // staged lines i in [i0, i1): input y = ybase + i (zero line when outside); rows z in [zlo, zhi)
-                const int sy = seg2 ? 1 : a.sy;
-                const int ybase = T.my0 * sy - a.hy;
-                const int i0 = seg2 ? a.hy : 0, i1 = seg2 ? a.hy + a.YL : a.BY;
-                const int zlo = max(T.mz0 - a.hz, 0), zhi = min(T.mz0 + a.LZ + a.hz, a.Zin);
-                const uint32_t row_bytes = (uint32_t)(zhi - zlo) * 16;
-                const int ncopy = (i1 - i0) * 4;
-                // with several z tiles the border halo rows must be rewritten as zeros
-                const bool zl = a.ntz > 1 && a.hz > 0 && T.mz0 - a.hz < 0, zh = a.ntz > 1 && a.hz > 0 && T.mz0 + a.LZ + a.hz > a.Zin;
-                if (lane == 0) {
-                    // XT > 1: the plane feeds all x taps, so the stage carries the weights of every tap
-                    const uint32_t bb = seg2 ? a.b2_bytes : (a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes);
-                    mbar_expect_tx(full + st, (uint32_t)ncopy * (row_bytes + (zl ? 16u : 0u) + (zh ? 16u : 0u)) + bb);
-                    const uint8_t* wsrc = seg2 ? a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes
-                                               : a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + (a.XT > 1 ? 0 : j)) * a.b_bytes;
-                    bulk_load(base + a.b_off, wsrc, bb, full + st);
+            for (int q = T.q_lo; q <= T.q_hi; ++q) {
+                const int rs = q - jc;
+                const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                for (int cs = 0; cs < a.nchunk + n2; ++cs) {
+                    const bool seg2 = cs >= a.nchunk;
+                    const int c = seg2 ? cs - a.nchunk : cs;
+                    const int x = seg2 ? T.mx + rs : T.mx * a.sx + q + a.xoff;
+                    const int st = it % a.nstage;
+                    const long long t0 = a.dbg ? clock64() : 0;
+                    mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+                    if (a.dbg) t_wait += clock64() - t0;
+                    const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                    const vsseg_act8& src = seg2 ? a.in2 : a.in;
+                    // staged lines i in [i0, i1): input y = ybase + i (zero line when outside); rows z in [zlo, zhi)
+                    const int sy = seg2 ? 1 : a.sy;
+                    const int ybase = T.my0 * sy - a.hy;
+                    const int i0 = seg2 ? a.hy : 0, i1 = seg2 ? a.hy + a.YL : a.BY;
+                    const int zlo = max(T.mz0 - a.hz, 0), zhi = min(T.mz0 + a.LZ + a.hz, a.Zin);
+                    const uint32_t row_bytes = (uint32_t)(zhi - zlo) * 16;
+                    const int ncopy = (i1 - i0) * 4;
+                    // with several z tiles the border halo rows must be rewritten as zeros
+                    const bool zl = a.ntz > 1 && a.hz > 0 && T.mz0 - a.hz < 0, zh = a.ntz > 1 && a.hz > 0 && T.mz0 + a.LZ + a.hz > a.Zin;
+                    if (lane == 0) {
+                        // XT > 1: the plane feeds all x taps, so the stage carries the weights of every tap
+                        const uint32_t bb = seg2 ? a.b2_bytes : (a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes);
+                        mbar_expect_tx(full + st, (uint32_t)ncopy * (row_bytes + (zl ? 16u : 0u) + (zh ? 16u : 0u)) + bb);
+                        const uint8_t* wsrc = seg2 ? a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes
+                                                   : a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + (a.XT > 1 ? 0 : q)) * a.b_bytes;
+                        bulk_load(base + a.b_off, wsrc, bb, full + st);
+                    }
+                    const __nv_bfloat16* g0 = (const __nv_bfloat16*)src.hi + (int64_t)T.b * src.batch_stride;
+                    for (int k = lane; k < ncopy; k += 32) {
+                        const int i = i0 + (k >> 2), plane = (k >> 1) & 1, cg = k & 1;
+                        const int y = ybase + i;
+                        const void* gp = (y >= 0 && y < a.Yin)
+                                             ? (const void*)(g0 + (int64_t)plane * src.lo_offset +
+                                                             ((((int64_t)(2 * c + cg) * a.Xin + x) * a.Yin + y) * a.Zin + zlo) * 8)
+                                             : (const void*)g_zero_line;
+                        const uint32_t line = base + (uint32_t)plane * a.a_plane + (uint32_t)cg * a.lbo_a + (uint32_t)(i * a.pitch) * 16;
+                        bulk_load(line + (uint32_t)(zlo - (T.mz0 - a.hz)) * 16, gp, row_bytes, full + st);
+                        if (zl) bulk_load(line, g_zero_line, 16, full + st);
+                        if (zh) bulk_load(line + (uint32_t)(a.pitch - 1) * 16, g_zero_line, 16, full + st);
+                    }
+                    __syncwarp();
+                    ++it;
                 }
-                const __nv_bfloat16* g0 = (const __nv_bfloat16*)src.hi + (int64_t)T.b * src.batch_stride;
-                for (int q = lane; q < ncopy; q += 32) {
-                    const int i = i0 + (q >> 2), plane = (q >> 1) & 1, cg = q & 1;
-                    const int y = ybase + i;
-                    const void* gp = (y >= 0 && y < a.Yin)
-                                         ? (const void*)(g0 + (int64_t)plane * src.lo_offset +
-                                                         ((((int64_t)(2 * c + cg) * a.Xin + x) * a.Yin + y) * a.Zin + zlo) * 8)
-                                         : (const void*)g_zero_line;
-                    const uint32_t line = base + (uint32_t)plane * a.a_plane + (uint32_t)cg * a.lbo_a + (uint32_t)(i * a.pitch) * 16;
-                    bulk_load(line + (uint32_t)(zlo - (T.mz0 - a.hz)) * 16, gp, row_bytes, full + st);
-                    if (zl) bulk_load(line, g_zero_line, 16, full + st);
-                    if (zh) bulk_load(line + (uint32_t)(a.pitch - 1) * 16, g_zero_line, 16, full + st);
-                }
-                __syncwarp();
-                ++it;
             }
+        }
+        if (a.dbg && lane == 0) {
+            a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)t_wait;
+            a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_beg);
         }
     } else if (warp == 0) {
         if (elect_one()) {
             // ===== TMA producer =====
             int it = 0;
+            long long t_wait = 0, t_beg = clock64();
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const TcTile T = decode_tile(a, tile);
-                for (int s = 0; s < ntot; ++s) {
-                    const bool seg2 = s >= nmain;
-                    const int c = seg2 ? (s - nmain) / a.XT : s / a.npl, j = seg2 ? 0 : s % a.npl;
-                    const int x = seg2 ? T.mx + (s - nmain) % a.XT : T.mx * a.sx + j + a.xoff;
-                    if (x < 0 || x >= a.Xin || j >= T.njx) continue;  // plane is padding: stage skipped on both sides
-                    const int st = it % a.nstage;
-                    mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
-                    const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-                    const CUtensorMap* map = seg2 ? &tmap2 : &tmap;
-                    const int cgp = seg2 ? a.cg_plane2 : a.cg_plane;
-                    const int cgi = T.b * (seg2 ? a.cg_batch2 : a.cg_batch) + c * 2;
-                    if (!seg2) {
-                        const uint32_t bb = a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes;
-                        mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + bb);
-                        for (int i = 0; i < a.nbox; ++i) {
-                            const uint32_t dst = base + (uint32_t)a.boxes[i].dst16 * 16;
-                            const int zc = T.mz0 * a.sz + a.boxes[i].dz, yc = T.my0 * a.sy + a.boxes[i].dy;
-                            tma_box(a.map_wide, dst, map, full + st, zc, yc, x, cgi);
-                            tma_box(a.map_wide, dst + a.a_plane, map, full + st, zc, yc, x, cgi + cgp);
+                for (int q = T.q_lo; q <= T.q_hi; ++q) {
+                    const int rs = q - jc;
+                    const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                    for (int cs = 0; cs < a.nchunk + n2; ++cs) {
+                        const bool seg2 = cs >= a.nchunk;
+                        const int c = seg2 ? cs - a.nchunk : cs;
+                        const int x = seg2 ? T.mx + rs : T.mx * a.sx + q + a.xoff;
+                        const int st = it % a.nstage;
+                        const long long t0 = a.dbg ? clock64() : 0;
+                        mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+                        if (a.dbg) t_wait += clock64() - t0;
+                        const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                        const CUtensorMap* map = seg2 ? &tmap2 : &tmap;
+                        const int cgp = seg2 ? a.cg_plane2 : a.cg_plane;
+                        const int cgi = T.b * (seg2 ? a.cg_batch2 : a.cg_batch) + c * 2;
+                        if (a.dbgf & 2) {
+                            mbar_arrive(full + st);
+                        } else if (!seg2) {
+                            const uint32_t bb = a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes;
+                            mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + bb);
+                            for (int i = 0; i < a.nbox; ++i) {
+                                const uint32_t dst = base + (uint32_t)a.boxes[i].dst16 * 16;
+                                const int zc = T.mz0 * a.sz + a.boxes[i].dz, yc = T.my0 * a.sy + a.boxes[i].dy;
+                                tma_box(a.map_wide, dst, map, full + st, zc, yc, x, cgi);
+                                tma_box(a.map_wide, dst + a.a_plane, map, full + st, zc, yc, x, cgi + cgp);
+                            }
+                            bulk_load(base + a.b_off, a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + (a.XT > 1 ? 0 : q)) * a.b_bytes, bb,
+                                      full + st);
+                        } else {
+                            // shortcut source: same box shape, unshifted in z, 1x1x1 weights
+                            mbar_expect_tx(full + st, 2 * a.box_tx + a.b2_bytes);
+                            const int zc = T.mz0 + a.dz2, yc = T.my0 + a.dy2;
+                            tma_box(a.map_wide, base, map, full + st, zc, yc, x, cgi);
+                            tma_box(a.map_wide, base + a.a_plane, map, full + st, zc, yc, x, cgi + cgp);
+                            bulk_load(base + a.b_off, a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes, a.b2_bytes, full + st);
                         }
-                        bulk_load(base + a.b_off, a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + (a.XT > 1 ? 0 : j)) * a.b_bytes, bb,
-                                  full + st);
-                    } else {
-                        // shortcut source: same box shape, unshifted in z, 1x1x1 weights
-                        mbar_expect_tx(full + st, 2 * a.box_tx + a.b2_bytes);
-                        const int zc = T.mz0 + a.dz2, yc = T.my0 + a.dy2;
-                        tma_box(a.map_wide, base, map, full + st, zc, yc, x, cgi);
-                        tma_box(a.map_wide, base + a.a_plane, map, full + st, zc, yc, x, cgi + cgp);
-                        bulk_load(base + a.b_off, a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes, a.b2_bytes, full + st);
+                        ++it;
                     }
-                    ++it;
                 }
             }
+            if (a.dbg) {
+                a.dbg[blockIdx.x * 8 + 3] = (unsigned long long)t_wait;
+                a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_beg);
+            }
         }
-    } else if (warp == 1) {
+    } else if (warp < TC_EPI_WARP0) {
+        const int mw = warp - 1;   // this issuer owns the rows g with g % TC_MMA_WARPS == mw
         if (elect_one()) {
             // ===== MMA issuer (one elected lane; every MMA accumulates into TMEM zeroed by the epilogue warps) =====
-            int it = 0, k = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+            int it = 0, rowbase = 0;
+            long long t_full = 0, t_acc = 0, n_mma = 0, t_beg = clock64();
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const TcTile T = decode_tile(a, tile);
-                const int buf = k % a.nbuf;
-                mbar_wait(acc_empty + buf, (k / a.nbuf) & 1);   // drained and re-zeroed by the epilogue warps
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)buf * buf_cols;
-                for (int s = 0; s < ntot; ++s) {
-                    const bool seg2 = s >= nmain;
-                    const int j = seg2 ? 0 : s % a.npl;
-                    const int x = seg2 ? T.mx + (s - nmain) % a.XT : T.mx * a.sx + j + a.xoff;
-                    if (x < 0 || x >= a.Xin || j >= T.njx) continue;
-                    const int st = it % a.nstage;
-                    mbar_wait(full + st, (it / a.nstage) & 1);
-                    tc_fence_after();
-                    const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-                    const uint64_t da = make_desc(base, a.lbo_a, 128);
-                    if (!seg2) {
-                        const uint64_t db = make_desc(base + a.b_off, a.lbo_b, 128);
-                        if (a.XT == 1) {
-#pragma unroll 4
-                            for (int i = 0; i < a.nop; ++i) {
-                                const TcOp op = a.ops[i];
-                                umma_bf16(tacc + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
-                            }
-                        } else {
-                            // plane j of the haloed tile feeds output row r = j - dx through x tap dx
-                            for (int dx = 0; dx < a.nj; ++dx) {
-                                const int r = j - dx;
-                                if (r < 0 || r >= a.XT) continue;
-                                const uint32_t tr = tacc + (uint32_t)r * row_cols;
-                                const uint64_t dbx = db + (uint64_t)(dx * (a.b_bytes >> 4));
-#pragma unroll 4
-                                for (int i = 0; i < a.nop; ++i) {
-                                    const TcOp op = a.ops[i];
-                                    umma_bf16(tr + op.col, da + op.a16, dbx + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
+                int opened = 0;
+                for (int q = T.q_lo; q <= T.q_hi; ++q) {
+                    // rows 0..min(q, xt-1) receive MMAs from this plane on: their slots must be drained and re-zeroed
+                    const int need = min(q, T.xt - 1);
+                    if (opened <= need) {
+                        const long long t0 = a.dbg ? clock64() : 0;
+                        for (; opened <= need; ++opened) {
+                            const int g = rowbase + opened;
+                            mbar_wait(acc_empty + g % R, (g / R) & 1);
+                        }
+                        tc_fence_after();
+                        if (a.dbg) t_acc += clock64() - t0;
+                    }
+                    const int rs = q - jc;
+                    const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                    for (int cs = 0; cs < a.nchunk + n2; ++cs) {
+                        const bool seg2 = cs >= a.nchunk;
+                        const int st = it % a.nstage;
+                        const long long t0 = a.dbg ? clock64() : 0;
+                        mbar_wait(full + st, (it / a.nstage) & 1);
+                        tc_fence_after();
+                        if (a.dbg) { t_full += clock64() - t0; n_mma += seg2 ? a.nop2 : a.nop * (a.XT == 1 ? 1 : min(q, T.xt - 1) - max(q - njm1, 0) + 1); }   // all issuers' MMAs
+                        const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                        const uint32_t da = (base & 0x3FFFF) >> 4, db = ((base + a.b_off) & 0x3FFFF) >> 4;   // stage start, 16 B units
+                        const uint32_t dh = a.desc_hi;
+                        if (!seg2) {
+                            const uint32_t ap = a.a_plane >> 4, bp = a.b_plane >> 4;
+                            const int nel = a.nop / 3;
+                            if (a.XT == 1) {
+                                const uint32_t tr = tmem_base + (uint32_t)(rowbase % R) * slot_cols;
+#pragma unroll 2
+                                for (int i = rowbase % TC_MMA_WARPS == mw ? 0 : nel; i < nel; ++i) {
+                                    const TcEl e = a.el[i];
+                                    const uint32_t al = e.a_lo + da, bl = e.b_lo + db, t = tr + e.col;
+                                    umma_bf16_w(t, al, dh, bl, dh, e.idesc);
+                                    umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
+                                    umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                }
+                            } else {
+                                // plane q of the haloed tile feeds output row r = q - dx through x tap dx
+                                for (int dx = 0; dx < a.nj; ++dx) {
+                                    const int r = q - dx;
+                                    if (r < 0 || r >= T.xt || (rowbase + r) % TC_MMA_WARPS != mw) continue;
+                                    const uint32_t tr = tmem_base + (uint32_t)((rowbase + r) % R) * slot_cols;
+                                    const uint32_t dbx = db + (uint32_t)dx * (a.b_bytes >> 4);
+#pragma unroll 2
+                                    for (int i = 0; i < nel; ++i) {
+                                        const TcEl e = a.el[i];
+                                        const uint32_t al = e.a_lo + da, bl = e.b_lo + dbx, t = tr + e.col;
+                                        umma_bf16_w(t, al, dh, bl, dh, e.idesc);
+                                        umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
+                                        umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                    }
                                 }
                             }
+                        } else {
+                            const uint32_t ap = a.a_plane >> 4, bp = a.b2_plane >> 4;
+                            const uint32_t tr = tmem_base + (uint32_t)((rowbase + rs) % R) * slot_cols + row_cols;
+                            for (int i = (rowbase + rs) % TC_MMA_WARPS == mw ? 0 : a.nop2 / 3; i < a.nop2 / 3; ++i) {
+                                const TcEl e = a.el2[i];
+                                const uint32_t al = e.a_lo + da, bl = e.b_lo + db, t = tr + e.col;
+                                umma_bf16_w(t, al, dh, bl, dh, e.idesc);
+                                umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
+                                umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                            }
                         }
-                    } else {
-                        const uint64_t db = make_desc(base + a.b_off, a.lbo_b2, 128);
-                        const uint32_t tr = tacc + (uint32_t)a.XT * row_cols + (uint32_t)((s - nmain) % a.XT) * row_cols;
-                        for (int i = 0; i < a.nop2; ++i) {
-                            const TcOp op = a.ops2[i];
-                            umma_bf16(tr + op.col, da + op.a16, db + op.b16, a.idesc | ((uint32_t)op.n8 << 17), 1u);
-                        }
+                        umma_commit(empty + st);
+                        ++it;
                     }
-                    umma_commit(empty + st);
-                    ++it;
+                    // rows whose last plane this was are complete
+                    const int r0 = max(q - njm1, 0), r1 = q == T.q_hi ? T.xt - 1 : q - njm1;
+                    for (int r = r0; r <= r1; ++r) umma_commit(acc_full + (rowbase + r) % R);
                 }
-                umma_commit(acc_full + buf);
+                rowbase += T.xt;
+            }
+            if (a.dbg && mw == 0) {
+                a.dbg[blockIdx.x * 8 + 0] = (unsigned long long)t_full;
+                a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)t_acc;
+                a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)(clock64() - t_beg);
+                a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)n_mma;
             }
         }
     } else {
         // ===== epilogue: TC_EPI_WARPS warps, TMEM lanes (warp % 4) * 32 .. +31, thread = one M-tile row;
-        // the warps sharing a lane quadrant take alternate accumulators =====
+        // the warps sharing a lane quadrant take alternate (accumulator, 16-column) units of every row slot =====
         const int lane_base = (warp & 3) * 32;
-        const int esub = (warp - 2) >> 2, nsub = TC_EPI_WARPS / 4;
+        const int esub = (warp - TC_EPI_WARP0) >> 2, nsub = TC_EPI_WARPS / 4;
         const uint32_t tlane = tmem_base + ((uint32_t)lane_base << 16);
-        // zero this warp's lanes of every accumulator buffer, then release the MMA issuer
-        for (int bf = 0; bf < a.nbuf; ++bf) {
-            for (int ra = esub; ra < a.XT * a.nacc; ra += nsub)      // the accumulators this warp will drain
-                for (int c = 0; c < a.n_cta; c += 16) {
-                    tmem_st16_zero(tlane + (uint32_t)bf * buf_cols + (uint32_t)(ra * a.n_cta + c));
-                    if (a.nchunk2) tmem_st16_zero(tlane + (uint32_t)bf * buf_cols + (uint32_t)a.XT * row_cols + (uint32_t)(ra * a.n_cta + c));
-                }
+        const int n16 = a.n_cta >> 4;
+        constexpr bool sc = SC;
+        // zero this warp's lanes of the units it will drain in every slot, then release the MMA issuer
+        for (int sl = 0; sl < R; ++sl) {
+            for (int u = esub; u < a.nacc * n16; u += nsub) {
+                tmem_st16_zero(tlane + (uint32_t)sl * slot_cols + (uint32_t)(u * 16));
+                if (sc) tmem_st16_zero(tlane + (uint32_t)sl * slot_cols + row_cols + (uint32_t)(u * 16));
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + bf);
+            if (lane == 0) mbar_arrive(acc_empty + sl);
         }
-        const int r = lane_base + lane;
-        const int ly = r / a.LZ, zz = r % a.LZ;
+        const int rr_ = lane_base + lane;
+        const int ly = rr_ / a.LZ, zz = rr_ % a.LZ;
         const int Xo = a.out.X, Yo = a.out.Y, Zo = a.out.Z;
-        const uint32_t sc_col = (uint32_t)a.XT * row_cols;  // shortcut accumulators follow the main ones
-        __nv_bfloat16* out_hi = (__nv_bfloat16*)a.out.hi;
-        int k = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+        const int64_t cgs = (int64_t)Xo * Yo * Zo * 8;   // elements per 8-channel group
+        const int thr_off = (ly * a.uy * Zo + zz * a.uz) * 8;   // this thread's row of the M tile inside the output tile
+        const bool sig = a.ep.act == 1;
+        const float slope = a.ep.slope;
+        const int64_t lo_out = a.out.lo_offset, lo_res = a.res.lo_offset;
+        int rowbase = 0;
+        long long t_wait = 0, t_beg = clock64();
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const TcTile T = decode_tile(a, tile);
-            const int buf = k % a.nbuf;
-            const uint32_t tacc = tlane + (uint32_t)buf * buf_cols;
             const int b = T.b, my0 = T.my0, mz0 = T.mz0;
             const int co0 = T.ns * a.n_cta;
             const int nreal = min(a.n_cta, a.cout - co0);
-            mbar_wait(acc_full + buf, (k / a.nbuf) & 1);
-            tc_fence_after();
-            for (int ra = esub; ra < a.XT * a.nacc; ra += nsub) {
-                const int xr = ra / a.nacc, ai = ra - xr * a.nacc;
-                const int ox = (T.mx + xr) * a.ux + T.px;
-                // rows of a partial (zero-padded) line group load their TMEM lane like everyone else
-                // (tcgen05.ld is warp-collective) but neither read the residual nor store
-                const bool valid = my0 + ly + a.accs[ai].yl < a.Ym;
-                const int oy = (my0 + ly) * a.uy + a.accs[ai].y_add;
-                const int oz = (mz0 + zz) * a.uz + a.accs[ai].z_add;
-                float rsrc = 0.f;
-                if (a.res_mode == 2 && valid) rsrc = a.rsrc.ptr[b * a.rsrc.sb + ox * a.rsrc.sx + oy * a.rsrc.sy + oz * a.rsrc.sz];
-                for (int c0 = 0; c0 < nreal; c0 += 16) {
-                    uint32_t v[16], v2[16];
-                    const uint32_t taddr = tacc + (uint32_t)(ra * a.n_cta + c0);
-                    tmem_ld16(taddr, v);
-                    if (a.nchunk2) tmem_ld16(taddr + sc_col, v2);
+            // element offset (without batch and x) of this thread's voxel in accumulator 0, channel group co0/8
+            const int64_t tile_off = ((int64_t)(my0 * a.uy) * Zo + mz0 * a.uz) * 8 + thr_off + (int64_t)(co0 >> 3) * cgs;
+            __nv_bfloat16* const out_b = (__nv_bfloat16*)a.out.hi + (int64_t)b * a.out.batch_stride;
+            const __nv_bfloat16* const res_b = (const __nv_bfloat16*)a.res.hi + (int64_t)b * a.res.batch_stride;
+            for (int r = 0; r < T.xt; ++r) {
+                const int g = rowbase + r, slot = g % R;
+                const uint32_t tacc = tlane + (uint32_t)slot * slot_cols;
+                const int ox = (T.mx + r) * a.ux + T.px;
+                const int64_t row_off = tile_off + (int64_t)ox * Yo * Zo * 8;
+                const long long t0 = a.dbg ? clock64() : 0;
+                mbar_wait(acc_full + slot, (g / R) & 1);
+                tc_fence_after();
+                if (a.dbg) t_wait += clock64() - t0;
+                // units = (accumulator ai, 16-column chunk c), dealt to the quadrant's warps like the zeroing below
+                // (two units in flight per thread were tried: the extra registers spill and it is slower)
+                EpiCtx X{a, ep_c, tacc, row_cols, row_off, cgs, lo_out, lo_res, out_b, res_b, b, ox, my0, mz0, ly, zz, co0, nreal, sc, sig, slope};
+                int ai = 0, c = esub;
+                while (c >= n16) { c -= n16; ++ai; }
+                while (ai < a.nacc) {
+                    EpiUnit<SC, RM> U;
+                    U.ai = ai; U.c = c;
+                    c += nsub;
+                    while (c >= n16) { c -= n16; ++ai; }
+                    epi_load<OM, SC, RM>(X, U);
                     tmem_ld_wait();
-                    if (!valid) continue;
-                    if (a.out_mode == 1) {
-                        // planar fp32 output: attention map (sigmoid) or logits, optionally blended into the
-                        // sliding-window accumulator (MONAI sliding_window_inference step 6)
-                        const float sw = a.sw_weight ? __ldg(a.sw_weight + ((int64_t)ox * Yo + oy) * Zo + oz) : 0.f;
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {   // Cout <= 2 on this path (static indices keep v[] in registers)
-                            if (q >= a.cout) break;
-                            float f = __uint_as_float(v[q]) * ep_c[q] + ep_c[256 + q];
-                            f = apply_act(f, a.ep.act, a.ep.slope);
-                            float* o = a.outf.ptr + b * a.outf.sb + q * a.outf.sc + ox * a.outf.sx + oy * a.outf.sy + oz * a.outf.sz;
-                            if (a.sw_weight) *o += sw * f;
-                            else *o = f;
-                        }
-                        continue;
-                    }
-#pragma unroll
-                    for (int g8 = 0; g8 < 2; ++g8) {
-                        const int cc = co0 + c0 + g8 * 8;
-                        if (c0 + g8 * 8 >= nreal) break;
-                        float o[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float f = __uint_as_float(v[g8 * 8 + q]) * ep_c[cc + q] + ep_c[256 + cc + q];
-                            o[q] = apply_act(f, a.ep.act, a.ep.slope);
-                        }
-                        if (a.nchunk2) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) o[q] += __uint_as_float(v2[g8 * 8 + q]) + ep_c[512 + cc + q];
-                        }
-                        if (a.res_mode == 1) {
-                            const __nv_bfloat16* rp = (const __nv_bfloat16*)a.res.hi +
-                                                      act8_off(a.res.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
-                            float rr[8];
-                            unpack8(ldg128(rp), ldg128(rp + a.res.lo_offset), rr);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) o[q] += rr[q];
-                        } else if (a.res_mode == 2) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) o[q] += ep_c[768 + cc + q] * rsrc + ep_c[1024 + cc + q];
-                        }
-                        uint4 h, l;
-                        pack8(o, h, l);
-                        __nv_bfloat16* p = out_hi + act8_off(a.out.batch_stride, Xo, Yo, Zo, b, cc / 8, ox, oy, oz);
-                        *reinterpret_cast<uint4*>(p) = h;
-                        *reinterpret_cast<uint4*>(p + a.out.lo_offset) = l;
-                    }
+                    epi_finish<OM, SC, RM>(X, U);
                 }
-            }
-            // re-zero the drained buffer for its next tile and hand it back to the MMA issuer
-            if (tile + a.nbuf * (int)gridDim.x < a.ntiles) {
-                for (int ra = esub; ra < a.XT * a.nacc; ra += nsub)  // only the accumulators this warp drained
-                    for (int c = 0; c < a.n_cta; c += 16) {
-                        tmem_st16_zero(tacc + (uint32_t)(ra * a.n_cta + c));
-                        if (a.nchunk2) tmem_st16_zero(tacc + sc_col + (uint32_t)(ra * a.n_cta + c));
-                    }
+                // re-zero the drained units of the slot and hand it back to the MMA issuer
+                for (int u = esub; u < a.nacc * n16; u += nsub) {
+                    tmem_st16_zero(tacc + (uint32_t)(u * 16));
+                    if (sc) tmem_st16_zero(tacc + row_cols + (uint32_t)(u * 16));
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + buf);
+                if (lane == 0) mbar_arrive(acc_empty + slot);
             }
+            rowbase += T.xt;
+        }
+        if (a.dbg && warp == TC_EPI_WARP0 && lane == 0) {
+            a.dbg[blockIdx.x * 8 + 5] = (unsigned long long)t_wait;
+            a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_beg);
         }
     }
     tc_fence_before();
@@ -545,8 +746,8 @@ static bool gen_ops(const TcGeom& G, int YT, TcOp* ops, int* nop_out, TcAcc* acc
 
 // Fills the plan for (in -> out, geometry, n_split); returns false when the shape is not covered
 // (the caller then uses the generic CUDA-core kernel).
-static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int n_split,
-                      const vsseg_act8* src2, TcPlan* P) {
+static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int n_split,
+                               const vsseg_act8* src2, TcPlan* P) {
     if (!in || !out || !g || !in->hi || !out->hi) return false;
     if (in->C % 16 || out->C % 8 || in->B != out->B || n_split < 1) return false;
     const int KX = g->kx, KY = g->ky, KZ = g->kz;
@@ -602,21 +803,33 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     int best_nstage = 0;
     const int taps_stage = KY * KZ;
     const uint32_t b_bytes = (uint32_t)(2 * taps_stage * n_cta * 32);
-    // XT > 1 (several x rows per tile, stages = haloed x planes) cuts the 3x re-read of every input plane
-    // through L2; only for stride-1 convs with x taps, and only while a stage's weights stay small
-    const bool xt_ok = !tr && !strided && KX == 3 && (size_t)KX * b_bytes <= 40 * 1024;
-    static const int xt_max = getenv("VSSEG_TC_XT_MAX") ? atoi(getenv("VSSEG_TC_XT_MAX")) : 1;   // tuning knobs (measured: XT > 1 does not pay, the epilogue is the bottleneck)
+    // XT > 1: the CTA marches along x over XT rows and stages every input plane once for its (up to) three
+    // rows; stride-1 convs with x taps only.  A stage then carries the weights of all three x taps.
+    const bool xt_ok = !tr && !strided && KX == 3;
+    static const int xt_max = getenv("VSSEG_TC_XT_MAX") ? atoi(getenv("VSSEG_TC_XT_MAX")) : 64;   // tuning knobs
+    static const int xt_min = getenv("VSSEG_TC_XT_MIN") ? atoi(getenv("VSSEG_TC_XT_MIN")) : 1;
     static const int yt_max = getenv("VSSEG_TC_YT_MAX") ? atoi(getenv("VSSEG_TC_YT_MAX")) : 16;
-    for (int XT = 1; XT <= (xt_ok ? xt_max : 1); XT *= 2) {
-        if (Xm % XT) break;
-        const int npl = XT > 1 ? XT + KX - 1 : (tr ? 2 : KX);
-        const int stages_total = (tr ? (3 * (in->C / 16) + 1) / 2 : (in->C / 16) * npl) + (src2 ? (src2->C / 16) * XT : 0);
+    static const double fill_bpc = getenv("VSSEG_TC_FILL_BPC") ? atof(getenv("VSSEG_TC_FILL_BPC")) : 36.0;   // L2 -> shared bytes/cycle/SM
+    static const double epi_unit = getenv("VSSEG_TC_EPI_UNIT") ? atof(getenv("VSSEG_TC_EPI_UNIT")) : 400.0;  // cycles per (accumulator, 16 columns) unit per warp
+    int best_slots = 1;
+    const int sms_ = sm_count();
+    for (int XT = 1; XT <= (xt_ok ? (xt_max < Xm ? xt_max : Xm) : 1); ++XT) {
+        if (XT > 1 && XT < xt_min && xt_min <= Xm) continue;
+        const int nseg = (Xm + XT - 1) / XT;
+        if (XT > 1 && (Xm + nseg - 1) / nseg != XT) continue;   // keep the segments balanced
         const size_t bstage = round_up((int)((XT > 1 ? KX : 1) * b_bytes), 128);
-        const long total_tiles_1 = (long)in->B * (Xm / XT) * (Zm / LZ) * (tr ? 2 : 1) * n_split;
+        const long total_tiles_1 = (long)in->B * nseg * (Zm / LZ) * (tr ? 2 : 1) * n_split;
         for (int YT = 1; YT <= ygroups && YT <= yt_max; ++YT) {
             if (ygroups % YT) continue;
-            if (XT * YT * acc_mult * n_cta > 512) break;
+            const int cols1 = YT * acc_mult * n_cta;   // TMEM columns of one row slot
+            if (cols1 > 512) break;
             if (YT * acc_mult > TC_MAX_ACC) break;
+            // row slots: XT = 1 double-buffers whole tiles when two fit; the x march needs the three
+            // rows a plane feeds plus (ideally) one being drained
+            int slots = 512 / cols1;
+            if (XT == 1) slots = slots >= 2 ? 2 : 1;
+            else if (slots < 3) continue;
+            else if (slots > 6) slots = 6;
             int nbox, BY, BZ;
             if (line) { nbox = 1; BY = tr ? YT + 1 : (YT - 1) * sy_in + KY; BZ = LZ + 2 * hz; }
             else if (tr) { nbox = g->sz; BY = YT * LY + 1; BZ = LZ; }
@@ -637,26 +850,38 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
                     const double N = scratch[i].n8 * 8.0;
                     mma_cyc += N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
                 }
-                if (XT > 1) mma_cyc *= 3.0 * XT / (XT + 2);   // x taps served per plane stage, on average
             }
             const size_t stage = 2 * a_plane + bstage;
             if (stage / 16 >= 16000) break;
             const long budget = 227L * 1024 - TC_HDR;
             int nst = (int)(budget / (long)stage);
             if (nst < 2) break;
-            // cost model (persistent CTAs, one per SM): tiles per SM x tile time; tile time = main loop
-            // (stages x max(MMA cycles, smem fill at ~32 B/cycle/SM)) and epilogue, overlapped when the
-            // accumulators can be double-buffered in TMEM, serialised (plus pipeline refill) when not
+            // cost model (persistent CTAs, one per SM): waves x tile time.  Main loop: per staged plane-chunk
+            // max(MMA issue, shared-memory fill); epilogue: (accumulator, 16-column) units spread over the four
+            // warps of a TMEM lane quadrant; the two overlap when a row slot is free while the next fills
             const long tiles = total_tiles_1 * (ygroups / YT);
-            const bool dbuf = XT * YT * acc_mult * n_cta <= 256;
-            const double fill_cyc = (double)stage / 32.0;
-            const double stage_cyc = mma_cyc > fill_cyc ? mma_cyc : fill_cyc;
-            const double main_cyc = stages_total * stage_cyc;
-            const double epi_cyc = 300.0 + XT * YT * nphase * (n_cta / 16) * 260.0;
-            const double tile_cyc = dbuf ? (main_cyc > epi_cyc ? main_cyc : epi_cyc) + 200.0 : main_cyc + epi_cyc + 1500.0;
-            const double cost = (double)((tiles + 147) / 148) * tile_cyc + 4000.0;
+            const int nch = in->C / 16;
+            const double fill_cyc = (double)stage / fill_bpc;
+            double main_cyc;
+            if (XT > 1) {
+                const double per_plane = 3.0 * XT / (XT + 2) * mma_cyc;   // x taps served per staged plane, on average
+                main_cyc = (double)(XT + 2) * nch * (per_plane > fill_cyc ? per_plane : fill_cyc);
+            } else {
+                const double nst_main = tr ? 1.5 * nch : (double)nch * KX;
+                main_cyc = nst_main * (mma_cyc > fill_cyc ? mma_cyc : fill_cyc);
+            }
+            if (src2) {
+                const double f2 = (double)(2 * a_plane + 2 * n_cta * 32) / fill_bpc, m2 = YT * 3.0 * (32 + n_cta / 4.0);
+                main_cyc += (double)XT * (src2->C / 16) * (f2 > m2 ? f2 : m2);
+            }
+            const int units = YT * nphase * (n_cta / 16);
+            const double epi_cyc = XT * (150.0 + ((units + 3) / 4) * epi_unit);
+            const bool overlap = XT == 1 ? slots == 2 : slots >= 4;
+            const double tile_cyc = overlap ? (main_cyc > epi_cyc ? main_cyc : epi_cyc) + 300.0
+                                            : main_cyc + epi_cyc + (XT == 1 ? 1500.0 : 0.0);
+            const double cost = (double)((tiles + sms_ - 1) / sms_) * tile_cyc + 4000.0;
             if (cost < best_cost) {
-                best_cost = cost; best = YT; best_xt = XT; best_stage = stage;
+                best_cost = cost; best = YT; best_xt = XT; best_stage = stage; best_slots = slots;
                 best_nstage = nst > 6 ? 6 : nst;
             }
         }
@@ -688,8 +913,8 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     a.lbo_b2 = (uint32_t)(n_cta * 16);
     const TcGeom G{tr, strided, line, KY, KZ, LY, LZ, BZ, (int)g->sz, n_cta, sy_in, box_bytes, a.a_plane, a.b_plane};
     a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);   // N field (bits 17..22) comes from the op
-    a.ntz = Zm / LZ; a.nty = ygroups / YT; a.ntx = Xm / XT;
-    a.XT = XT; a.npl = XT > 1 ? XT + KX - 1 : (tr ? 2 : KX);
+    a.ntz = Zm / LZ; a.nty = ygroups / YT; a.ntx = (Xm + XT - 1) / XT;
+    a.XT = XT; a.Xm = Xm;
     a.npx = tr ? 2 : 1; a.nsplit = n_split; a.nsel = a.npx * n_split;
     a.LZ = LZ; a.LY = LY; a.YL = YT * LY; a.Ym = Ym;
     a.n_cta = n_cta; a.cout = out->C;
@@ -740,10 +965,27 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
         a.dy2 = -hy;
         a.dz2 = 0;
     }
+    {
+        // descriptor words (sm_100 K-major SWIZZLE_NONE: start >> 4 | LBO >> 4 << 16 ; SBO >> 4 | version 1 << 14).
+        // gen_ops emits the three passes of a merged product back to back; pass 0 carries the plane-0 offsets
+        a.desc_hi = (128u >> 4) | (1u << 14);
+        for (int i = 0; i < a.nop / 3; ++i) {
+            const TcOp& o = a.ops[3 * i];
+            a.el[i] = {o.a16 + (((a.lbo_a >> 4) & 0x3FFFu) << 16), o.b16 + (((a.lbo_b >> 4) & 0x3FFFu) << 16), o.col,
+                       a.idesc | ((uint32_t)o.n8 << 17)};
+        }
+        for (int i = 0; i < a.nop2 / 3; ++i) {
+            const TcOp& o = a.ops2[3 * i];
+            a.el2[i] = {o.a16 + (((a.lbo_a >> 4) & 0x3FFFu) << 16), o.b16 + (((a.lbo_b2 >> 4) & 0x3FFFu) << 16), o.col,
+                        a.idesc | ((uint32_t)o.n8 << 17)};
+        }
+        a.partial = (Ym % LY) != 0 ? 1 : 0;
+        for (int i = 0; i < a.nacc; ++i) a.accs[i].off8 = (a.accs[i].y_add * out->Z + a.accs[i].z_add) * 8;
+    }
     a.ntiles = (int)((long)in->B * a.ntx * a.nty * a.ntz * a.nsel);
     const int sms = sm_count();
-    const int cols1 = XT * nacc * (src2 ? 2 : 1) * n_cta;
-    a.nbuf = (cols1 <= 256 && a.ntiles > sms) ? 2 : 1;   // double-buffered accumulators when a CTA walks several tiles
+    const int cols1 = nacc * (src2 ? 2 : 1) * n_cta;
+    a.nbuf = best_slots;   // TMEM row slots
     const int cols = cols1 * a.nbuf;
     a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     P->box[0] = 8; P->box[1] = (cuuint32_t)(BZ * (strided ? g->sz : 1)); P->box[2] = (cuuint32_t)(BY * (strided ? g->sy : 1));
@@ -753,6 +995,43 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     P->smem = TC_HDR + (size_t)a.nstage * a.stage_bytes;
     P->grid = (unsigned)(a.ntiles < sms ? a.ntiles : sms);   // persistent: one CTA per SM
     return true;
+}
+
+// The tile search walks a few hundred candidates: plans are cached per shape (everything but the
+// base pointers).  Calls are serialised by the host thread that drives the stream.
+struct TcKey {
+    int64_t v[26];
+    bool operator==(const TcKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+static void key_act(const vsseg_act8* t, int64_t* v) {
+    v[0] = t->lo_offset; v[1] = t->batch_stride; v[2] = t->B; v[3] = t->C; v[4] = t->X; v[5] = t->Y; v[6] = t->Z;
+}
+static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int n_split,
+                      const vsseg_act8* src2, TcPlan* P) {
+    if (!in || !out || !g || !in->hi || !out->hi) return false;
+    TcKey k;
+    memset(&k, 0, sizeof(k));
+    key_act(in, k.v); key_act(out, k.v + 7);
+    if (src2) key_act(src2, k.v + 14);
+    k.v[21] = src2 ? 1 : 0;
+    k.v[22] = g->kx | (g->ky << 4) | (g->kz << 8) | (g->sx << 12) | (g->sy << 16) | (g->sz << 20) | ((g->transposed ? 1 : 0) << 24);
+    k.v[23] = n_split;
+    struct Entry { TcKey k; bool ok; TcPlan p; };
+    static std::vector<Entry>* cache = new std::vector<Entry>();
+    for (const Entry& e : *cache)
+        if (e.k == k) {
+            if (!e.ok) return false;
+            *P = e.p;
+            P->a.in = *in; P->a.out = *out;
+            if (src2) P->a.in2 = *src2;
+            return true;
+        }
+    Entry e;
+    e.k = k;
+    e.ok = make_plan_uncached(in, out, g, n_split, src2, &e.p);
+    if (cache->size() < 4096) cache->push_back(e);
+    if (e.ok) *P = e.p;
+    return e.ok;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -798,17 +1077,56 @@ static int encode_map(CUtensorMap* tmap, const vsseg_act8* t, int cg_plane, int 
     return 0;
 }
 
+// epilogue flavours are compile-time (out mode, fused shortcut, residual mode): the dead paths cost registers
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcArgs);
+static TcKernel pick_kernel(const TcArgs& a) {
+    const bool sc = a.nchunk2 != 0;
+    if (a.out_mode == 1) return conv_tc_kernel<1, false, 0>;
+    if (sc) return a.res_mode == 0 ? conv_tc_kernel<0, true, 0> : a.res_mode == 1 ? conv_tc_kernel<0, true, 1> : conv_tc_kernel<0, true, 2>;
+    return a.res_mode == 0 ? conv_tc_kernel<0, false, 0> : a.res_mode == 1 ? conv_tc_kernel<0, false, 1> : conv_tc_kernel<0, false, 2>;
+}
 static int set_smem_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) {
-            set_error("conv3d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return (int)e;
+        const TcKernel all[] = {conv_tc_kernel<1, false, 0>, conv_tc_kernel<0, true, 0>, conv_tc_kernel<0, true, 1>, conv_tc_kernel<0, true, 2>,
+                                conv_tc_kernel<0, false, 0>, conv_tc_kernel<0, false, 1>, conv_tc_kernel<0, false, 2>};
+        for (TcKernel k : all) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) {
+                set_error("conv3d_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return (int)e;
+            }
         }
         attr_set = true;
     }
     return 0;
+}
+
+// VSSEG_TC_DEBUG=1: every launch is followed by a synchronous dump of the per-role cycle counters
+static void launch_tc(const TcPlan& P, const CUtensorMap& tmap, const CUtensorMap& tmap2, TcArgs& a, cudaStream_t stream,
+                      const char* what) {
+    static const bool debug = getenv("VSSEG_TC_DEBUG") && atoi(getenv("VSSEG_TC_DEBUG"));
+    static unsigned long long* dbuf = nullptr;
+    a.dbg = nullptr;
+    a.dbgf = debug && getenv("VSSEG_TC_DBGF") ? atoi(getenv("VSSEG_TC_DBGF")) : 0;
+    if (debug) {
+        if (!dbuf) cudaMalloc(&dbuf, 256 * 8 * sizeof(unsigned long long));
+        cudaMemsetAsync(dbuf, 0, 256 * 8 * sizeof(unsigned long long), stream);
+        a.dbg = dbuf;
+    }
+    pick_kernel(a)<<<P.grid, TC_THREADS, P.smem, stream>>>(tmap, tmap2, a);
+    if (debug) {
+        static unsigned long long h[256 * 8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
+        double s[8] = {0};
+        for (unsigned i = 0; i < P.grid; ++i)
+            for (int k = 0; k < 8; ++k) s[k] += (double)h[i * 8 + k] / P.grid;
+        fprintf(stderr, "[tc-debug] %s cin=%d cout=%d X=%d XT=%d YL=%d slots=%d nstage=%d grid=%u | mma: total %.0f wait_full %.0f wait_acc %.0f n_mma %.0f "
+                        "(%.1f cyc/mma busy) | prod: total %.0f wait_empty %.0f | epi: total %.0f wait_full %.0f\n",
+                what, a.nchunk * 16, a.cout, a.out.X, a.XT, a.YL, a.nbuf, a.nstage, P.grid, s[2], s[0], s[1], s[7],
+                s[7] > 0 ? (s[2] - s[0] - s[1]) / s[7] : 0.0, s[4], s[3], s[6], s[5]);
+    }
 }
 
 }  // namespace vsseg
@@ -866,7 +1184,7 @@ int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const
     if (a.line_mode) memset(&tmap, 0, sizeof(tmap));
     else if (int e = encode_map(&tmap, in, a.cg_plane, a.cg_batch, P)) return e;
     if (int e = set_smem_attr()) return e;
-    conv_tc_kernel<<<P.grid, TC_THREADS, P.smem, (cudaStream_t)stream>>>(tmap, tmap, a);
+    launch_tc(P, tmap, tmap, a, (cudaStream_t)stream, "f32out");
     return check_launch("conv3d_tc_f32out");
 }
 
@@ -930,7 +1248,7 @@ int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_con
         }
     }
     if (int e = set_smem_attr()) return e;
-    conv_tc_kernel<<<P.grid, TC_THREADS, P.smem, (cudaStream_t)stream>>>(tmap, tmap2, a);
+    launch_tc(P, tmap, tmap2, a, (cudaStream_t)stream, "conv");
     return check_launch("conv3d_tc");
 }
 

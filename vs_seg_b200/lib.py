@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsseg_b200.so")
+LIB_PATH = os.environ.get("VSSEG_LIB_PATH") or os.path.join(_HERE, "libvsseg_b200.so")  # override: kernel-variant experiments
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 
