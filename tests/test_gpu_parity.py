@@ -138,6 +138,52 @@ def test_unet_eval_matches_oracle_shapes(shape):
         assert a.shape == r.shape and (a.cpu() - r).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("levels", [1, 3, 5])
+def test_window_group_plan_equals_single_window_plans(levels):
+    """A window-group plan (fine levels per window, coarse levels batched) must reproduce the
+    single-window plan bit for bit - logits, blended accumulation and attention maps."""
+    from vs_seg_b200.tensors import f32view
+    sd = unet_oracle.seeded_state_dict(5)
+    net = _native_net(sd)
+    roi, nwin = (64, 64, 16), 3
+    vol = torch.randn((1, 1, 96, 64, 24), generator=torch.Generator().manual_seed(31)).to(_dev())
+    starts = [(0, 0, 0), (32, 0, 8), (16, 0, 4)]
+    wmap = torch.rand(roi, generator=torch.Generator().manual_seed(32)).to(_dev())
+    one = net.eval_plan(roi, batch=1)
+    grp = net.eval_plan(roi, batch=nwin, window_levels=levels)
+    assert grp.window_levels == levels
+    acc1 = torch.zeros((1, 2, 96, 64, 24), device=_dev())
+    acc2 = torch.zeros_like(acc1)
+    atts1 = []
+    for s_ in starts:
+        one.run(f32view(vol, s_, roi), f32view(acc1, s_, roi), wmap.data_ptr())
+        atts1.append([a.clone() for a in one.att_maps])
+    grp.run([f32view(vol, s_, roi) for s_ in starts], [f32view(acc2, s_, roi) for s_ in starts], wmap.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(acc1, acc2)
+    for i in range(nwin):
+        for a1, a2 in zip(atts1[i], grp.att_maps):
+            assert torch.equal(a1[0], a2[i])
+    # plain forward of a window batch
+    x = torch.stack([vol[0, :, s_[0]:s_[0] + 64, s_[1]:s_[1] + 64, s_[2]:s_[2] + 16] for s_ in starts]).contiguous()
+    got = grp.forward(x)[0]
+    ref = torch.cat([one.forward(x[i:i + 1])[0] for i in range(nwin)])
+    assert torch.equal(got, ref)
+
+
+def test_sliding_window_ragged_groups(monkeypatch):
+    """Group sizes that do not divide the window count (and group = 1) give the same volume."""
+    from vs_seg_b200.sliding_window import sliding_window_inference
+    net = _native_net(unet_oracle.seeded_state_dict(4))
+    x = torch.randn((1, 1, 96, 80, 24), generator=torch.Generator().manual_seed(21)).to(_dev())
+    outs = []
+    for group in ("1", "3", "4"):
+        monkeypatch.setenv("VSSEG_SW_GROUP", group)
+        with torch.no_grad():
+            outs.append(sliding_window_inference(x, (64, 64, 16), 1, net, mode="gaussian"))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_unet_rejects_indivisible_shape_and_train_mode():
     sd = unet_oracle.seeded_state_dict(3)
     net = _native_net(sd)

@@ -19,11 +19,18 @@ def main():
     dev = torch.device("cuda:0")
     net, _ = bench.build_net(dev)
     roi = bench.ROI
-    plan = net.eval_plan(roi, 1, dev)
+    group = int(os.environ.get("PROFILE_GROUP", "1"))   # > 1: a window-group plan (per-patch = total / group)
     vol = torch.randn((1, 1) + bench.VOLUME, device=dev)
     acc = torch.zeros((1, 2) + bench.VOLUME, device=dev)
     imap = sw.importance_map(roi, "gaussian", 0.125, dev)
-    prof = plan.profile(f32view(vol, (0, 0, 0), roi), f32view(acc, (0, 0, 0), roi), imap.data_ptr(), iters=5)
+    if group > 1:
+        plan = net.eval_plan(roi, group, dev, window_levels=int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "3")))
+        starts = sw.window_starts(bench.VOLUME, roi, 0.25)[:group]
+        prof = plan.profile([f32view(vol, s, roi) for s in starts], [f32view(acc, s, roi) for s in starts],
+                            imap.data_ptr(), iters=5)
+    else:
+        plan = net.eval_plan(roi, 1, dev)
+        prof = plan.profile(f32view(vol, (0, 0, 0), roi), f32view(acc, (0, 0, 0), roi), imap.data_ptr(), iters=5)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     tot = sum(p[4] for p in prof)

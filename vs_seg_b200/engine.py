@@ -132,9 +132,15 @@ def _conv_cost(src, dst, k, transposed, cin, cout, extra_elems=0):
 
 
 class UNetEvalPlan:
-    """Flat launch list for one patch shape [B,1,X,Y,Z] (X,Y % 32 == 0, Z % 8 == 0)."""
+    """Flat launch list for one patch shape [B,1,X,Y,Z] (X,Y % 32 == 0, Z % 8 == 0).
 
-    def __init__(self, state_dict, patch_size, batch=1, device="cuda:0", attention=True,
+    ``window_levels`` = d > 0 makes the B entries independent WINDOWS (sliding-window groups): the d
+    finest levels are launched per window on its own source/destination view (each such launch already
+    fills the GPU), the coarser levels once for all B windows - their launches are latency-bound on a
+    single window (a few dozen CTAs, K walked serially), so B windows cost about the same as one.
+    """
+
+    def __init__(self, state_dict, patch_size, batch=1, device="cuda:0", attention=True, window_levels=0,
                  channels=(16, 32, 48, 64, 80, 96),
                  strides=((2, 2, 1), (2, 2, 1), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
                  kernel_sizes=((3, 3, 1), (3, 3, 1), (3, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
@@ -164,9 +170,14 @@ class UNetEvalPlan:
         self._keep = []  # device tensors referenced by raw pointers
         self.steps = []
         self.att_maps = []  # fp32 [B,1,x,y,z] tensors, coarsest first (hook order)
-        # the two per-call descriptors (mutated in place by run())
-        self.src = _lib.F32View()
-        self.dst = _lib.F32View()
+        # the per-call descriptors (mutated in place by run()): one pair for the whole batch, or one pair
+        # per window when the fine levels run per window
+        self.window_levels = max(0, min(int(window_levels), len(channels) - 1)) if self.B > 1 else 0
+        nview = self.B if self.window_levels else 1
+        self.srcs = [_lib.F32View() for _ in range(nview)]
+        self.dsts = [_lib.F32View() for _ in range(nview)]
+        self.src, self.dst = self.srcs[0], self.dsts[0]
+        self._bs = (0, self.B)   # batch slice the step being emitted works on
         self.sw_weight = C.c_void_p(None)
         self._build()
 
@@ -184,6 +195,10 @@ class UNetEvalPlan:
         self._keep.append(b)
         return b
 
+    def _v(self, buf, c0=0, C_=None):
+        """View of the batch slice the current step works on."""
+        return buf.view(c0, C_, self._bs[0], self._bs[1])
+
     def _add_conv(self, name, p, src, dst, k, stride=(1, 1, 1), transposed=False, norm=True, act="prelu",
                   res=None, res_cin1=None, shortcut=None):
         """src/dst: Act8 views.  One fused Convolution block (+ optional residual).
@@ -197,7 +212,7 @@ class UNetEvalPlan:
         ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
         g = self._geom(k, stride, transposed)
         res_p = C.byref(res) if res is not None else None
-        tail = (None, C.byref(self.src), res_cin1[0].data_ptr(), res_cin1[1].data_ptr()) if res_cin1 is not None \
+        tail = (None, C.byref(self._cur_src()), res_cin1[0].data_ptr(), res_cin1[1].data_ptr()) if res_cin1 is not None \
             else (res_p, None, None, None)
         self._keep += [src, dst, g, ep, res]
         extra = _nvox(dst) * cout if res is not None else (_nvox(dst) if res_cin1 is not None else 0)
@@ -229,6 +244,15 @@ class UNetEvalPlan:
         args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), cpad, C.byref(ep)) + tail
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
         return False
+
+    def _tag(self):
+        return f"@w{self._bs[0]}" if self.window_levels and self._bs[1] == 1 else ""
+
+    def _cur_src(self):
+        return self.srcs[self._bs[0]] if self.window_levels and self._bs[1] == 1 else self.srcs[0]
+
+    def _cur_dst(self):
+        return self.dsts[self._bs[0]] if self.window_levels and self._bs[1] == 1 else self.dsts[0]
 
     @staticmethod
     def _pad_cout(w, transposed, c):
@@ -285,11 +309,14 @@ class UNetEvalPlan:
         """AttentionBlock1+2 on act8 buffer `buf` (all channels), in place.  The hidden tensor uses a
         multiple of 16 channels (zero weights for the padding) so both convs run on tensor cores."""
         cin = buf.C
-        src, h = buf.view(), hid.view(0, _round_up(cin // 2, 16))
+        src, h = self._v(buf), self._v(hid, 0, _round_up(cin // 2, 16))
         self._add_conv(name + ".conv1", p + "0.conv1.", src, h, k, norm=False, act="relu")
-        att = torch.empty((self.B, 1, buf.X, buf.Y, buf.Z), dtype=torch.float32, device=self.device)
-        self.att_maps.append(att)
-        av = f32view(att)
+        key = name.split("@")[0]   # one map per gate, shared by the per-window steps
+        att = self._att.get(key)
+        if att is None:
+            att = self._att[key] = torch.empty((self.B, 1, buf.X, buf.Y, buf.Z), dtype=torch.float32, device=self.device)
+            self.att_maps.append(att)
+        av = f32view(att[self._bs[0]:self._bs[0] + self._bs[1]])
         self._add_smallcout(name + ".conv2", h, av, k, self.sd[p + "0.conv2.conv.weight"],
                             self.sd[p + "0.conv2.conv.bias"], 1, 0.0)
         self.steps.append(_Step(name + ".gate", self.lib.vsseg_att_gate, (C.byref(src), C.byref(av), C.byref(src)),
@@ -303,7 +330,7 @@ class UNetEvalPlan:
         cout = dst.C
         sc = (p + "residual.", src)
         last = p + f"conv.unit{subunits - 1}."
-        last_src = src if subunits == 1 else h_buf.view(0, cout)
+        last_src = src if subunits == 1 else self._v(h_buf, 0, cout)
         if subunits == 2:
             self._add_conv(name + ".unit0", p + "conv.unit0.", src, last_src, k)
         n0 = len(self.steps)
@@ -311,7 +338,7 @@ class UNetEvalPlan:
             return
         # not fused: drop the step just added and redo it with an explicit shortcut launch
         del self.steps[n0:]
-        r = r_buf.view(0, cout)
+        r = self._v(r_buf, 0, cout)
         self._add_shortcut(name + ".residual", p + "residual.", src, r)
         self._add_conv(name + f".unit{subunits - 1}", last, last_src, dst, k, res=r)
 
@@ -336,10 +363,13 @@ class UNetEvalPlan:
         for l in range(nlev - 1):
             prefixes.append(p)
             p = p + "1.submodule.1."
-        # ---- encoder
-        for l in range(nlev - 1):
+        self._att = {}
+        v = self._v
+
+        def encoder(l):
             p, k, sk, s = prefixes[l], self.kernel_sizes[l], self.sample_kernel_sizes[l], self.strides[l]
-            e = cat[l].view(0, ch[l])
+            tag = self._tag()
+            e = v(cat[l], 0, ch[l])
             if l == 0:
                 # unit0 reads the 1-channel fp32 source in place; the 1x1x1 shortcut (Cin=1) is an
                 # affine map of the same source applied in unit1's epilogue.
@@ -349,40 +379,31 @@ class UNetEvalPlan:
                 scale, shift = self._dev(scale), self._dev(shift)
                 ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, code)
                 g = self._geom(k)
-                h = hb[0].view()
+                h = v(hb[0])
                 self._keep += [ep, g, h]
                 fl, nb = _conv_cost(h, h, k, False, 1, ch[0])
-                self.steps.append(_Step("enc0.unit0", self.lib.vsseg_conv3d_cin1,
-                                        (C.byref(self.src), C.byref(h), C.byref(g), w.data_ptr(), C.byref(ep)),
+                self.steps.append(_Step("enc0.unit0" + tag, self.lib.vsseg_conv3d_cin1,
+                                        (C.byref(self._cur_src()), C.byref(h), C.byref(g), w.data_ptr(), C.byref(ep)),
                                         fl, nb - 4 * _nvox(h) * (ch[0] - 1)))
                 rw = self._dev(self.sd[p + "0.residual.weight"].reshape(-1).float())
                 rbias = self._dev(self.sd[p + "0.residual.bias"].float())
-                self._add_conv("enc0.unit1", p + "0.conv.unit1.", h, e, k, res_cin1=(rw, rbias))
+                self._add_conv("enc0.unit1" + tag, p + "0.conv.unit1.", h, e, k, res_cin1=(rw, rbias))
             else:
-                self._add_ru(f"enc{l}", p + "0.", dn[l - 1].view(), hb[l], rb[l], e, k, 2)
-            self._add_conv(f"down{l}", p + "1.submodule.0.", e, dn[l].view(), sk, stride=s)
-        # ---- bottom
-        pb = prefixes[-1] + "1.submodule.1."
-        kb = self.kernel_sizes[-1]
-        if self.attention:
-            self._add_att("bottom.att", pb + "0.", dn[-1], bot_hid, kb)
-            self._add_ru("bottom", pb + "1.", dn[-1].view(), bot_h, bot_r, bot_o.view(), kb, 2)
-        else:
-            self._add_ru("bottom", pb, dn[-1].view(), bot_h, bot_r, bot_o.view(), kb, 2)
-        # ---- decoder
-        sub_out = bot_o.view()
-        for l in range(nlev - 2, -1, -1):
+                self._add_ru(f"enc{l}" + tag, p + "0.", v(dn[l - 1]), hb[l], rb[l], e, k, 2)
+            self._add_conv(f"down{l}" + tag, p + "1.submodule.0.", e, v(dn[l]), sk, stride=s)
+
+        def decoder(l):
             p, k, sk, s = prefixes[l], self.kernel_sizes[l], self.sample_kernel_sizes[l], self.strides[l]
-            self._add_conv(f"up{l}", p + "1.submodule.2.", sub_out, cat[l].view(ch[l], ch[l]), sk, stride=s,
+            tag = self._tag()
+            sub_out = v(hb[l + 1], 0, ch[l + 1]) if l + 1 < nlev - 1 else v(bot_o)
+            self._add_conv(f"up{l}" + tag, p + "1.submodule.2.", sub_out, v(cat[l], ch[l], ch[l]), sk, stride=s,
                            transposed=True)
             pr = p + "2."
             if self.attention:
-                self._add_att(f"dec{l}.att", pr + "0.", cat[l], hb[l], k)
+                self._add_att(f"dec{l}.att" + tag, pr + "0.", cat[l], hb[l], k)
                 pr = pr + "1."
             if l > 0:
-                out = hb[l].view(0, ch[l])
-                self._add_ru(f"dec{l}", pr, cat[l].view(), None, rb[l], out, k, 1)
-                sub_out = out
+                self._add_ru(f"dec{l}" + tag, pr, v(cat[l]), None, rb[l], v(hb[l], 0, ch[l]), k, 1)
             else:
                 # top unit: conv_only + shortcut, both linear -> one conv (shortcut folded into the
                 # centre tap), written to planar fp32 or blended into the sliding-window accumulator.
@@ -390,29 +411,66 @@ class UNetEvalPlan:
                 w[:, :, k[0] // 2, k[1] // 2, k[2] // 2] += self.sd[pr + "residual.weight"].reshape(
                     self.out_channels, -1).float()
                 bias = self.sd[pr + "conv.unit0.conv.bias"] + self.sd[pr + "residual.bias"]
-                src = cat[0].view()
+                src = v(cat[0])
                 # bytes: out read-modify-write + weight map instead of a plain store
-                self._add_smallcout("dec0.logits", src, self.dst, k, w, bias, 0, 1.0, self.sw_weight,
+                self._add_smallcout("dec0.logits" + tag, src, self._cur_dst(), k, w, bias, 0, 1.0, self.sw_weight,
                                     nb_extra=4 * _nvox(src) * (self.out_channels + 1))
+
+        d = self.window_levels
+        windows = [(i, 1) for i in range(self.B)] if d else []
+        # ---- fine levels of the encoder, window by window
+        for bs in windows:
+            self._bs = bs
+            for l in range(d):
+                encoder(l)
+        # ---- coarse levels, all windows at once
+        self._bs = (0, self.B)
+        for l in range(d, nlev - 1):
+            encoder(l)
+        pb = prefixes[-1] + "1.submodule.1."
+        kb = self.kernel_sizes[-1]
+        if self.attention:
+            self._add_att("bottom.att", pb + "0.", dn[-1], bot_hid, kb)
+            self._add_ru("bottom", pb + "1.", v(dn[-1]), bot_h, bot_r, v(bot_o), kb, 2)
+        else:
+            self._add_ru("bottom", pb, v(dn[-1]), bot_h, bot_r, v(bot_o), kb, 2)
+        for l in range(nlev - 2, d - 1, -1):
+            decoder(l)
+        # ---- fine levels of the decoder, window by window
+        for bs in windows:
+            self._bs = bs
+            for l in range(d - 1, -1, -1):
+                decoder(l)
+        self._bs = (0, self.B)
         del self.sd
 
     # -- execution ----------------------------------------------------------------------
     def _set(self, view, new):
         C.memmove(C.byref(view), C.byref(new), C.sizeof(_lib.F32View))
 
-    def run(self, src: _lib.F32View, dst: _lib.F32View, sw_weight_ptr: int | None = None, stream=None):
+    def _bind(self, src, dst, sw_weight_ptr):
+        srcs = list(src) if isinstance(src, (list, tuple)) else [src]
+        dsts = list(dst) if isinstance(dst, (list, tuple)) else [dst]
+        nb = 1 if self.window_levels else self.B
+        if len(srcs) != len(self.srcs) or len(dsts) != len(self.dsts):
+            raise ValueError(f"run(): the plan takes {len(self.srcs)} source/destination view(s)")
+        for s_, d_ in zip(srcs, dsts):
+            if (s_.B, s_.X, s_.Y, s_.Z) != (nb, *self.patch) or (d_.B, d_.C, d_.X, d_.Y, d_.Z) != (
+                    nb, self.out_channels, *self.patch):
+                raise ValueError("run(): view shapes do not match the plan")
+        for mine, new in zip(self.srcs + self.dsts, srcs + dsts):
+            self._set(mine, new)
+        self.sw_weight.value = sw_weight_ptr
+
+    def run(self, src, dst, sw_weight_ptr: int | None = None, stream=None):
         """Launch the whole forward for one patch batch.
 
         src: [B,1,X,Y,Z] fp32 region (may be a strided window of a larger volume);
         dst: [B,out_channels,X,Y,Z] fp32 region; if ``sw_weight_ptr`` is given the logits are
-        blended (dst += weight * logits) instead of stored.
+        blended (dst += weight * logits) instead of stored.  A plan built with ``window_levels`` takes
+        lists of B single-window views instead.
         """
-        if (src.B, src.X, src.Y, src.Z) != (self.B, *self.patch) or (dst.B, dst.C, dst.X, dst.Y, dst.Z) != (
-                self.B, self.out_channels, *self.patch):
-            raise ValueError("run(): view shapes do not match the plan")
-        self._set(self.src, src)
-        self._set(self.dst, dst)
-        self.sw_weight.value = sw_weight_ptr
+        self._bind(src, dst, sw_weight_ptr)
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         for st in self.steps:
             code = st.fn(*st.args, s)
@@ -422,9 +480,7 @@ class UNetEvalPlan:
 
     def profile(self, src, dst, sw_weight_ptr=None, iters=3):
         """Per-step device time (ms, mean of `iters`, CUDA events on the launch stream)."""
-        self._set(self.src, src)
-        self._set(self.dst, dst)
-        self.sw_weight.value = sw_weight_ptr
+        self._bind(src, dst, sw_weight_ptr)
         stream = torch.cuda.current_stream(self.device)
         s = stream.cuda_stream
         ms = [0.0] * len(self.steps)
@@ -452,7 +508,10 @@ class UNetEvalPlan:
         if x.device != self.device or x.dtype != torch.float32:
             raise ValueError("forward(): expects a float32 tensor on the plan's device")
         out = torch.empty((self.B, self.out_channels, *self.patch), dtype=torch.float32, device=self.device)
-        self.run(f32view(x), f32view(out))
+        if self.window_levels:
+            self.run([f32view(x[i:i + 1]) for i in range(self.B)], [f32view(out[i:i + 1]) for i in range(self.B)])
+        else:
+            self.run(f32view(x), f32view(out))
         return out, list(self.att_maps)
 
 

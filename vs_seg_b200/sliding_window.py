@@ -16,6 +16,8 @@ Two paths:
 """
 from __future__ import annotations
 
+import os
+
 import itertools
 import math
 from typing import Callable, Sequence
@@ -149,11 +151,22 @@ def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="c
     if model is not None and inputs.is_cuda and nd == 3:
         if inputs.dtype != torch.float32:
             inputs = inputs.float()
-        plan = model.eval_plan(roi_size, batch=1, device=inputs.device)
-        acc = torch.zeros((batch, plan.out_channels) + image_size, dtype=torch.float32, device=inputs.device)
+        # windows run in groups: the fine levels of the net window by window (each launch fills the GPU),
+        # the coarse levels once per group (latency-bound launches, see UNetEvalPlan).  Every window still
+        # reads its input in place and blends its logits straight into the accumulator.
+        group = max(1, int(os.environ.get("VSSEG_SW_GROUP", "4")))
+        levels = int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "3"))
+        acc = torch.zeros((batch, model.out_channels) + image_size, dtype=torch.float32, device=inputs.device)
         wptr = imap.data_ptr()
-        for b, s in jobs:
-            plan.run(f32view(inputs[b:b + 1], s, roi_size), f32view(acc[b:b + 1], s, roi_size), wptr)
+        for g0 in range(0, len(jobs), group):
+            grp = jobs[g0:g0 + group]
+            srcs = [f32view(inputs[b:b + 1], s, roi_size) for b, s in grp]
+            dsts = [f32view(acc[b:b + 1], s, roi_size) for b, s in grp]
+            if len(grp) == 1:
+                model.eval_plan(roi_size, batch=1, device=inputs.device).run(srcs[0], dsts[0], wptr)
+            else:
+                plan = model.eval_plan(roi_size, batch=len(grp), device=inputs.device, window_levels=levels)
+                plan.run(srcs, dsts, wptr)
         return acc, cnt, lows, image_size_
     acc = None
     for g0 in range(0, len(jobs), sw_batch_size):

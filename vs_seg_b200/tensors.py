@@ -27,12 +27,16 @@ class Act8Buffer:
     def nvox(self):
         return self.X * self.Y * self.Z
 
-    def view(self, c0=0, C=None) -> _lib.Act8:
+    def view(self, c0=0, C=None, b0=0, nb=None) -> _lib.Act8:
+        """Channel range [c0, c0+C) of batch entries [b0, b0+nb) (pointer offsets only)."""
         C = self.C - c0 if C is None else C
+        nb = self.B - b0 if nb is None else nb
         if c0 % 8 or C % 8 or c0 + C > self.C:
             raise ValueError("act8 views must be aligned to 8 channels")
-        return _lib.Act8(self.t.data_ptr() + (c0 // 8) * self.nvox * 8 * 2,
-                         self.B * self.C * self.nvox, self.C * self.nvox, self.B, C, self.X, self.Y, self.Z)
+        if b0 < 0 or nb < 1 or b0 + nb > self.B:
+            raise ValueError("act8 view outside the batch")
+        return _lib.Act8(self.t.data_ptr() + ((c0 // 8) * self.nvox * 8 + b0 * self.C * self.nvox) * 2,
+                         self.B * self.C * self.nvox, self.C * self.nvox, nb, C, self.X, self.Y, self.Z)
 
     def to_ncdhw(self, c0=0, C=None) -> torch.Tensor:
         """fp32 [B,C,X,Y,Z] copy through the native unpack kernel."""
