@@ -24,7 +24,7 @@ def main():
     acc = torch.zeros((1, 2) + bench.VOLUME, device=dev)
     imap = sw.importance_map(roi, "gaussian", 0.125, dev)
     if group > 1:
-        plan = net.eval_plan(roi, group, dev, window_levels=int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "3")))
+        plan = net.eval_plan(roi, group, dev, window_levels=int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1")))
         starts = sw.window_starts(bench.VOLUME, roi, 0.25)[:group]
         prof = plan.profile([f32view(vol, s, roi) for s in starts], [f32view(acc, s, roi) for s in starts],
                             imap.data_ptr(), iters=5)

@@ -154,8 +154,8 @@ def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="c
         # windows run in groups: the fine levels of the net window by window (each launch fills the GPU),
         # the coarse levels once per group (latency-bound launches, see UNetEvalPlan).  Every window still
         # reads its input in place and blends its logits straight into the accumulator.
-        group = max(1, int(os.environ.get("VSSEG_SW_GROUP", "4")))
-        levels = int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "3"))
+        group = max(1, int(os.environ.get("VSSEG_SW_GROUP", "8")))
+        levels = int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"))
         acc = torch.zeros((batch, model.out_channels) + image_size, dtype=torch.float32, device=inputs.device)
         wptr = imap.data_ptr()
         for g0 in range(0, len(jobs), group):
