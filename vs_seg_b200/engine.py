@@ -366,10 +366,13 @@ class UNetEvalPlan:
         self._att = {}
         v = self._v
 
-        def encoder(l):
+        def encoder(l, part="all"):
             p, k, sk, s = prefixes[l], self.kernel_sizes[l], self.sample_kernel_sizes[l], self.strides[l]
             tag = self._tag()
             e = v(cat[l], 0, ch[l])
+            if part == "down":
+                self._add_conv(f"down{l}" + tag, p + "1.submodule.0.", e, v(dn[l]), sk, stride=s)
+                return
             if l == 0:
                 # unit0 reads the 1-channel fp32 source in place; the 1x1x1 shortcut (Cin=1) is an
                 # affine map of the same source applied in unit1's epilogue.
@@ -390,18 +393,23 @@ class UNetEvalPlan:
                 self._add_conv("enc0.unit1" + tag, p + "0.conv.unit1.", h, e, k, res_cin1=(rw, rbias))
             else:
                 self._add_ru(f"enc{l}" + tag, p + "0.", v(dn[l - 1]), hb[l], rb[l], e, k, 2)
-            self._add_conv(f"down{l}" + tag, p + "1.submodule.0.", e, v(dn[l]), sk, stride=s)
+            if part != "units":
+                self._add_conv(f"down{l}" + tag, p + "1.submodule.0.", e, v(dn[l]), sk, stride=s)
 
-        def decoder(l):
+        def decoder(l, part="all"):
             p, k, sk, s = prefixes[l], self.kernel_sizes[l], self.sample_kernel_sizes[l], self.strides[l]
             tag = self._tag()
             sub_out = v(hb[l + 1], 0, ch[l + 1]) if l + 1 < nlev - 1 else v(bot_o)
-            self._add_conv(f"up{l}" + tag, p + "1.submodule.2.", sub_out, v(cat[l], ch[l], ch[l]), sk, stride=s,
-                           transposed=True)
+            if part != "out":
+                self._add_conv(f"up{l}" + tag, p + "1.submodule.2.", sub_out, v(cat[l], ch[l], ch[l]), sk, stride=s,
+                               transposed=True)
             pr = p + "2."
             if self.attention:
-                self._add_att(f"dec{l}.att" + tag, pr + "0.", cat[l], hb[l], k)
+                if part != "out":
+                    self._add_att(f"dec{l}.att" + tag, pr + "0.", cat[l], hb[l], k)
                 pr = pr + "1."
+            if part == "upatt":
+                return
             if l > 0:
                 self._add_ru(f"dec{l}" + tag, pr, v(cat[l]), None, rb[l], v(hb[l], 0, ch[l]), k, 1)
             else:
@@ -418,13 +426,18 @@ class UNetEvalPlan:
 
         d = self.window_levels
         windows = [(i, 1) for i in range(self.B)] if d else []
+        # with d = 1 only the launches that touch a window's own source / destination view run per window
+        # (first ResidualUnit, logits conv); the rest of the finest level is batched like the coarse ones
+        split0 = d == 1
         # ---- fine levels of the encoder, window by window
         for bs in windows:
             self._bs = bs
             for l in range(d):
-                encoder(l)
+                encoder(l, "units" if split0 else "all")
         # ---- coarse levels, all windows at once
         self._bs = (0, self.B)
+        if split0:
+            encoder(0, "down")
         for l in range(d, nlev - 1):
             encoder(l)
         pb = prefixes[-1] + "1.submodule.1."
@@ -436,11 +449,13 @@ class UNetEvalPlan:
             self._add_ru("bottom", pb, v(dn[-1]), bot_h, bot_r, v(bot_o), kb, 2)
         for l in range(nlev - 2, d - 1, -1):
             decoder(l)
+        if split0:
+            decoder(0, "upatt")
         # ---- fine levels of the decoder, window by window
         for bs in windows:
             self._bs = bs
             for l in range(d - 1, -1, -1):
-                decoder(l)
+                decoder(l, "out" if split0 else "all")
         self._bs = (0, self.B)
         del self.sd
 
