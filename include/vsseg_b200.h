@@ -127,6 +127,12 @@ int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, c
  * w_packed: as vsseg_conv3d_tc with n_split = 1 and Cout zero-padded to 16; ep->scale/shift: [16]. */
 int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g,
                            const void* w_packed, const vsseg_epilogue* ep, const float* sw_weight, void* stream);
+/* Same operation with the "two-pass" weight image: with C = Cout <= 2 real output channels the 16 weight
+ * columns of plane 0 hold [bf16 hi(W) (C columns) | bf16 lo(W) (C columns) | 0] and plane 1 holds
+ * [bf16 hi(W) | 0].  The kernel then needs two MMAs per product instead of three
+ * (A_hi x plane 0, A_lo x plane 1) and the epilogue adds column C+q to column q: same bf16x3 value. */
+int vsseg_conv3d_tc_f32out_2p(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g,
+                              const void* w_packed, const vsseg_epilogue* ep, const float* sw_weight, void* stream);
 
 /* Human-readable description of the launch plan (tile, stages, op table) for tests and DESIGN.md. */
 int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,

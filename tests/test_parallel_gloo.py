@@ -58,3 +58,18 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
         spans = [shard_range(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_shard_slab_covers_the_shard_windows():
+    from vs_seg_b200.parallel import shard_slab
+    from vs_seg_b200.sliding_window import shard_range, window_starts
+    img, roi = (384, 384, 160), (128, 128, 128)
+    starts = window_starts(img, roi, 0.25)
+    assert len(starts) == 32
+    for world in (1, 2, 4, 8, 5):
+        for r in range(world):
+            lo, hi = shard_range(len(starts), r, world)
+            x0, x1 = shard_slab(img, roi, 0.25, r, world)
+            assert all(x0 <= s[0] and s[0] + roi[0] <= x1 for s in starts[lo:hi])
+    assert shard_slab(img, roi, 0.25, 0, 8) == (0, 128) and shard_slab(img, roi, 0.25, 7, 8) == (256, 384)
+    assert shard_slab((64, 64, 16), (64, 64, 16), 0.25, 0, 2) is None   # one window, two ranks: rank 1 owns it

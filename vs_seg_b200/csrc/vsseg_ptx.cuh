@@ -28,6 +28,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// same wait with a suspend-time hint: the waiting warp sleeps in hardware instead of re-issuing try_wait (the
+// epilogue / producer warps' spin loops took ~10 % of the issue slots the MMA-issuing warps compete for)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_R:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_R;\n"
+        "bra WAIT_LOOP_R;\n"
+        "DONE_R:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(4000u)
+        : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,

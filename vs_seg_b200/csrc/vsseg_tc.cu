@@ -103,6 +103,7 @@ struct TcArgs {
     TcEl el2[TC_MAX_OPS2 / 3];
     uint32_t desc_hi;          // upper descriptor word (SBO = 128 B, version 1)
     int partial;               // the last y line group is partial (rows beyond Ym are masked)
+    int two_pass;              // Cout <= 2 planar output: weights packed [hi | lo] along N, two MMAs per product
 };
 
 constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
@@ -221,7 +222,9 @@ __device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) 
 #pragma unroll
         for (int q = 0; q < 2; ++q) {   // Cout <= 2 on this path (static indices keep v[] in registers)
             if (q >= a.cout) break;
-            float f = __uint_as_float(U.v[q]) * ep_c[q] + ep_c[256 + q];
+            float raw = __uint_as_float(U.v[q]);
+            if (a.two_pass) raw += __uint_as_float(a.cout == 1 ? U.v[q + 1] : U.v[q + 2]);   // + hi*lo partial sums
+            float f = raw * ep_c[q] + ep_c[256 + q];
             f = apply_act(f, a.ep.act, X.slope);
             float* o = a.outf.ptr + X.b * a.outf.sb + q * a.outf.sc + X.ox * a.outf.sx + U.oy * a.outf.sy + U.oz * a.outf.sz;
             if (a.sw_weight) *o += sw * f;
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     const int x = seg2 ? T.mx + rs : T.mx * a.sx + q + a.xoff;
                     const int st = it % a.nstage;
                     const long long t0 = a.dbg ? clock64() : 0;
-                    mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+                    mbar_wait_relaxed(empty + st, ((it / a.nstage) & 1) ^ 1);
                     if (a.dbg) t_wait += clock64() - t0;
                     const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
                     const vsseg_act8& src = seg2 ? a.in2 : a.in;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                         const int x = seg2 ? T.mx + rs : T.mx * a.sx + q + a.xoff;
                         const int st = it % a.nstage;
                         const long long t0 = a.dbg ? clock64() : 0;
-                        mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
+                        mbar_wait_relaxed(empty + st, ((it / a.nstage) & 1) ^ 1);
                         if (a.dbg) t_wait += clock64() - t0;
                         const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
                         const CUtensorMap* map = seg2 ? &tmap2 : &tmap;
@@ -494,6 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                         const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
                         const uint32_t da = (base & 0x3FFFF) >> 4, db = ((base + a.b_off) & 0x3FFFF) >> 4;   // stage start, 16 B units
                         const uint32_t dh = a.desc_hi;
+                        const bool tp = a.two_pass != 0;   // (A_hi, [W_hi | W_lo]) and (A_lo, [W_hi | 0]) instead of three passes
                         if (!seg2) {
                             const uint32_t ap = a.a_plane >> 4, bp = a.b_plane >> 4;
                             const int nel = a.nop / 3;
@@ -504,8 +508,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                     const TcEl e = a.el[i];
                                     const uint32_t al = e.a_lo + da, bl = e.b_lo + db, t = tr + e.col;
                                     umma_bf16_w(t, al, dh, bl, dh, e.idesc);
-                                    umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
-                                    umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                    if (tp) {
+                                        umma_bf16_w(t, al + ap, dh, bl + bp, dh, e.idesc);
+                                    } else {
+                                        umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
+                                        umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                    }
                                 }
                             } else {
                                 // plane q of the haloed tile feeds output row r = q - dx through x tap dx
@@ -519,8 +527,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                         const TcEl e = a.el[i];
                                         const uint32_t al = e.a_lo + da, bl = e.b_lo + dbx, t = tr + e.col;
                                         umma_bf16_w(t, al, dh, bl, dh, e.idesc);
-                                        umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
-                                        umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                        if (tp) {
+                                            umma_bf16_w(t, al + ap, dh, bl + bp, dh, e.idesc);
+                                        } else {
+                                            umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
+                                            umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                        }
                                     }
                                 }
                             }
@@ -595,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 const int ox = (T.mx + r) * a.ux + T.px;
                 const int64_t row_off = tile_off + (int64_t)ox * Yo * Zo * 8;
                 const long long t0 = a.dbg ? clock64() : 0;
-                mbar_wait(acc_full + slot, (g / R) & 1);
+                mbar_wait_relaxed(acc_full + slot, (g / R) & 1);
                 tc_fence_after();
                 if (a.dbg) t_wait += clock64() - t0;
                 // units = (accumulator ai, 16-column chunk c), dealt to the quadrant's warps like the zeroing below
@@ -1163,8 +1175,8 @@ int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, c
     return best;
 }
 
-int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
-                           const vsseg_epilogue* ep, const float* sw_weight, void* stream) {
+static int tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
+                     const vsseg_epilogue* ep, const float* sw_weight, void* stream, int two_pass) {
     VSSEG_REQUIRE(in && out && out->ptr && out->C >= 1 && out->C <= 2, "conv3d_tc_f32out: Cout must be 1 or 2");
     // the plan only needs the output extents: describe the planar output as a 16-channel act8 tensor
     vsseg_act8 o16{};
@@ -1179,6 +1191,7 @@ int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const
     a.out_mode = 1;
     a.outf = *out;
     a.cout = out->C;
+    a.two_pass = two_pass;
     a.sw_weight = sw_weight;
     CUtensorMap tmap;
     if (a.line_mode) memset(&tmap, 0, sizeof(tmap));
@@ -1186,6 +1199,16 @@ int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const
     if (int e = set_smem_attr()) return e;
     launch_tc(P, tmap, tmap, a, (cudaStream_t)stream, "f32out");
     return check_launch("conv3d_tc_f32out");
+}
+
+int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
+                           const vsseg_epilogue* ep, const float* sw_weight, void* stream) {
+    return tc_f32out(in, out, g, w_packed, ep, sw_weight, stream, 0);
+}
+
+int vsseg_conv3d_tc_f32out_2p(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
+                              const vsseg_epilogue* ep, const float* sw_weight, void* stream) {
+    return tc_f32out(in, out, g, w_packed, ep, sw_weight, stream, 1);
 }
 
 int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int32_t n_split,

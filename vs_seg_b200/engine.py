@@ -50,7 +50,8 @@ def _split_planes(w: torch.Tensor) -> torch.Tensor:
     return torch.stack([hi, lo])
 
 
-def pack_conv_weight_tc(w: torch.Tensor, transposed: bool = False, n_split: int = 1, _flip_y: bool = True) -> torch.Tensor:
+def pack_conv_weight_tc(w: torch.Tensor, transposed: bool = False, n_split: int = 1, _flip_y: bool = True,
+                        _planes=None) -> torch.Tensor:
     """torch conv weight -> bf16 [sel][Cin/16][j][plane hi/lo][tz][khalf][ty'][n_cta][8], the shared-memory
     image vsseg_conv3d_tc streams with cp.async.bulk (layout documented in include/vsseg_b200.h).
     ty' = ky-1-ty for Conv3d (so the y taps that share an input line are adjacent N rows), ty for
@@ -69,8 +70,26 @@ def pack_conv_weight_tc(w: torch.Tensor, transposed: bool = False, n_split: int 
     n_cta = cp // n_split
     if _flip_y:
         w = w.flip(3)
-    p = _split_planes(w).reshape(2, n_split, n_cta, cin // 16, 2, 8, kx, ky, kz)  # plane sel n c khalf e j ty tz
+    planes = _split_planes(w) if _planes is None else _planes(w)
+    p = planes.reshape(2, n_split, n_cta, cin // 16, 2, 8, kx, ky, kz)  # plane sel n c khalf e j ty tz
     return p.permute(1, 3, 6, 0, 8, 4, 7, 2, 5).contiguous()  # sel c j plane tz khalf ty' n e
+
+
+def pack_conv_weight_tc_2p(w: torch.Tensor) -> torch.Tensor:
+    """Two-pass image for vsseg_conv3d_tc_f32out_2p (Cout <= 2): plane 0 columns = [hi(W) | lo(W) | 0],
+    plane 1 columns = [hi(W) | 0]; both planes hold exact bf16 values."""
+    c = w.shape[0]
+    if c > 8:
+        raise ValueError("two-pass packing needs Cout <= 8")
+
+    def planes(wp):   # wp: [16, Cin, kx, ky, kz] (zero-padded, y-flipped), rows 0..c-1 real
+        hl = _split_planes(wp[:c])
+        p0 = torch.zeros_like(wp, dtype=torch.bfloat16)
+        p1 = torch.zeros_like(p0)
+        p0[:c], p0[c:2 * c], p1[:c] = hl[0], hl[1], hl[0]
+        return torch.stack([p0, p1])
+
+    return pack_conv_weight_tc(w, False, 1, _planes=planes)
 
 
 def pack_shortcut_weight_tc(w: torch.Tensor, n_split: int = 1) -> torch.Tensor:
@@ -276,12 +295,12 @@ class UNetEvalPlan:
         if self.use_tc and src.C % 16 == 0:
             o16 = _lib.Act8(src.hi, 0, 0, src.B, 16, src.X, src.Y, src.Z)  # extents only (plan check)
             if self.lib.vsseg_conv3d_tc_supported(C.byref(src), C.byref(o16), C.byref(g), 1, None):
-                wp = self._dev(pack_conv_weight_tc(self._pad_cout(w, False, 16), False, 1))
+                wp = self._dev(pack_conv_weight_tc_2p(w))
                 scale = self._dev(torch.ones(16))
                 shift = self._dev(torch.nn.functional.pad(bias.float(), (0, 16 - cout)))
                 ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, act_code)
                 self._keep.append(ep)
-                self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc_f32out,
+                self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc_f32out_2p,
                                         (C.byref(src), C.byref(out_view), C.byref(g), wp.data_ptr(), C.byref(ep),
                                          sw_weight), fl, nb, kind="tcgen05"))
                 return
