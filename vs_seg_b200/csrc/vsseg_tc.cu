@@ -873,7 +873,10 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             // warps of a TMEM lane quadrant; the two overlap when a row slot is free while the next fills
             const long tiles = total_tiles_1 * (ygroups / YT);
             const int nch = in->C / 16;
-            const double fill_cyc = (double)stage / fill_bpc;
+            // a stage can only be refilled after its MMAs have drained: with a 2-deep ring the copy latency
+            // (~1500 cycles issue-to-arrival) is exposed on every stage, with 3+ it hides behind the other stages
+            static const double fill_lat = getenv("VSSEG_TC_FILL_LAT") ? atof(getenv("VSSEG_TC_FILL_LAT")) : 0.0;   // measured: a latency term makes the choice worse overall
+            const double fill_cyc = (double)stage / fill_bpc + (nst == 2 ? fill_lat : 0.0);
             double main_cyc;
             if (XT > 1) {
                 const double per_plane = 3.0 * XT / (XT + 2) * mma_cyc;   // x taps served per staged plane, on average
