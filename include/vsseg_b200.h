@@ -240,6 +240,15 @@ int vsseg_conv3d_smallcout_bwd(const vsseg_act8* x, const vsseg_f32view* dy, con
 int vsseg_att_gate_bwd(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_act8* dg,
                        const vsseg_act8* dx, const vsseg_f32view* datt, int32_t accumulate_dx, void* stream);
 
+/* ---- optimizer (reference params/VSparams.py:388-391, :457-463: torch.optim.Adam(lr, weight_decay) stepped
+ * once per batch over 178 tensors).  One launch over flat fp32 buffers of n elements (16-byte aligned):
+ *   g = grad * grad_scale + weight_decay * param;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   param -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)        (torch.optim.Adam, amsgrad off)
+ * grad_scale = 1 / world_size folds the data-parallel gradient average into the step. */
+int vsseg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -249,6 +249,9 @@ class VSparams:
 
     def cache_transformed_train_data(self, train_files, train_transforms):
         self.logger.info("Caching training data set...")
+        if self.world_size > 1:   # data-parallel: every rank trains on its own shard (DistributedSampler semantics)
+            from vs_seg_b200.ddp import shard_list
+            train_files = shard_list(train_files, self.rank, self.world_size)
         train_ds = dataio.CacheDataset(data=train_files, transform=train_transforms, cache_rate=1.0,
                                        num_workers=self.num_workers)
         return DataLoader(train_ds, batch_size=self.train_batch_size, shuffle=True, num_workers=self.num_workers,
@@ -293,7 +296,10 @@ class VSparams:
 
     def set_and_get_optimizer(self, model):
         self.logger.info("Setting up the optimizer...")
-        return torch.optim.Adam(model.parameters(), lr=self.initial_learning_rate, weight_decay=self.weight_decay)
+        # same interface as the reference's torch.optim.Adam (VSparams.py:388-391); CUDA parameters are stepped
+        # by one fused native launch over a flat buffer, CPU parameters by torch.optim.Adam itself
+        from vs_seg_b200.optim import FusedAdam
+        return FusedAdam(model.parameters(), lr=self.initial_learning_rate, weight_decay=self.weight_decay)
 
     def compute_dice_score(self, predicted_probabilities, label):
         """Hard foreground Dice of the argmax segmentation (reference VSparams.py:393-408)."""
@@ -318,6 +324,15 @@ class VSparams:
         best_metric, best_metric_epoch = -1, -1
         epoch_loss_values, metric_values = list(), list()
         num_epochs = self.num_epochs
+        # data-parallel training under torchrun: weights of rank 0 everywhere, one all-reduce of the flat
+        # gradient per step (vs_seg_b200.ddp); a single process is the reference's own loop
+        from vs_seg_b200 import ddp
+        if self.world_size > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group("nccl" if str(self.device).startswith("cuda") else "gloo")
+            ddp.broadcast_module_state(model)
+        reducer = ddp.GradReducer(model, optimizer)
         start = perf_counter()
         for epoch in range(num_epochs):
             logger.info("-" * 10)
@@ -336,12 +351,14 @@ class VSparams:
                 outputs = model(inputs)
                 loss = loss_function(outputs, labels)
                 loss.backward()
+                reducer.reduce()
                 optimizer.step()
-                epoch_loss += loss.item()
+                # the loss stays on the device (no host sync per step); it is read once per epoch / log line
+                epoch_loss = epoch_loss + loss.detach()
                 if epoch == 0:
                     logger.info("{}/{}, train_loss: {:.4f}".format(step, len(train_loader) // train_loader.batch_size,
                                                                    loss.item()))
-            epoch_loss /= step
+            epoch_loss = float(epoch_loss) / max(step, 1)
             epoch_loss_values.append(epoch_loss)
             logger.info("epoch {} average loss: {:.4f}".format(epoch + 1, epoch_loss))
 
@@ -369,7 +386,8 @@ class VSparams:
                         tb_writer.add_scalar("Dice Score Val", metric, epoch)
                     if metric > best_metric:
                         best_metric, best_metric_epoch = metric, epoch + 1
-                        torch.save(model.state_dict(), os.path.join(self.model_path, "best_metric_model.pth"))
+                        if self.rank == 0:   # the replicas hold identical weights
+                            torch.save(model.state_dict(), os.path.join(self.model_path, "best_metric_model.pth"))
                         logger.info("saved new best metric model")
                     logger.info("current epoch {} current mean dice: {:.4f} best mean dice: {:.4f} at epoch {}".format(
                         epoch + 1, metric, best_metric, best_metric_epoch))
@@ -381,7 +399,8 @@ class VSparams:
                         self.lr_divisor, param_group["lr"]))
 
         logger.info("Train completed, best_metric: {:.4f}  at epoch: {}".format(best_metric, best_metric_epoch))
-        torch.save(model.state_dict(), os.path.join(self.model_path, "last_epoch_model.pth"))
+        if self.rank == 0:
+            torch.save(model.state_dict(), os.path.join(self.model_path, "last_epoch_model.pth"))
         logger.info(f'Saved model of the last epoch at: {os.path.join(self.model_path, "last_epoch_model.pth")}')
         return epoch_loss_values, metric_values
 

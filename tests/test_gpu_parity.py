@@ -476,3 +476,37 @@ def test_tcgen05_wgrad_matches_torch(B, cin, cout, dims, k):
         got = dw[:, :, :cout].reshape(*k, cin, cout).permute(4, 3, 0, 1, 2).cpu().double()
         outs.append(got)
         assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item(), ("tc" if tc else "cuda-core")
+
+
+@pytest.mark.gpu
+def test_fused_adam_matches_torch_adam():
+    """vsseg_adam_step over the flat buffer vs torch.optim.Adam (reference VSparams.py:388-391 settings plus a
+    larger weight decay, an lr change through param_groups as VSparams.py:517-523 does, odd tensor sizes)."""
+    from vs_seg_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(16, 1, 3, 3, 1), (16,), (1,), (48, 32, 3, 3, 3), (7, 5), (2, 32, 1, 1, 1)]
+    ps_a = [torch.nn.Parameter(torch.randn(s, device=_dev())) for s in shapes]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    opt_a = FusedAdam(ps_a, lr=1e-2, weight_decay=1e-3)
+    opt_b = torch.optim.Adam(ps_b, lr=1e-2, weight_decay=1e-3)
+    v0 = [p._version for p in ps_a]
+    for it in range(6):
+        opt_a.zero_grad()
+        opt_b.zero_grad()
+        for pa, pb in zip(ps_a, ps_b):
+            g = torch.randn(pa.shape, device=_dev(), generator=None)
+            (pa * g).sum().backward()
+            (pb * g).sum().backward()
+        if it == 3:
+            for o in (opt_a, opt_b):
+                for grp in o.param_groups:
+                    grp["lr"] = grp["lr"] / 2
+        opt_a.step()
+        opt_b.step()
+    for pa, pb in zip(ps_a, ps_b):
+        assert (pa - pb).abs().max().item() < 2e-6 * (1 + pb.abs().max().item())
+    assert all(p._version > v for p, v in zip(ps_a, v0))      # cached eval plans see the update
+    # gradients of the next backward still land in the flat buffer after zero_grad()
+    opt_a.zero_grad()
+    (ps_a[0] * 2).sum().backward()
+    assert opt_a.flat_grads()[0][:ps_a[0].numel()].eq(2).all()

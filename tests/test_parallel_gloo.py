@@ -73,3 +73,45 @@ def test_shard_slab_covers_the_shard_windows():
             assert all(x0 <= s[0] and s[0] + roi[0] <= x1 for s in starts[lo:hi])
     assert shard_slab(img, roi, 0.25, 0, 8) == (0, 128) and shard_slab(img, roi, 0.25, 7, 8) == (256, 384)
     assert shard_slab((64, 64, 16), (64, 64, 16), 0.25, 0, 2) is None   # one window, two ranks: rank 1 owns it
+
+
+def _ddp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vs_seg_b200 import ddp
+    from vs_seg_b200.optim import FusedAdam
+    torch.manual_seed(100 + rank)           # different initial weights per rank: the broadcast must fix that
+    net = torch.nn.Sequential(torch.nn.Conv3d(1, 4, 3, padding=1), torch.nn.BatchNorm3d(4), torch.nn.PReLU(),
+                              torch.nn.Conv3d(4, 2, 1))
+    ddp.broadcast_module_state(net)
+    opt = FusedAdam(net.parameters(), lr=1e-2, weight_decay=1e-3)   # CPU parameters -> torch.optim.Adam inside
+    red = ddp.GradReducer(net, opt)
+    g = torch.Generator().manual_seed(7)
+    xs = torch.randn((4, 1, 8, 8, 4), generator=g)                  # global batch of 4, 2 per rank
+    x = xs[rank * 2:(rank + 1) * 2]
+    for _ in range(3):
+        opt.zero_grad()
+        net(x).square().mean().backward()
+        red.reduce()
+        opt.step()
+    torch.save({k: v.clone() for k, v in net.state_dict().items()}, out + f".{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_training_keeps_replicas_identical(tmp_path):
+    """Two gloo ranks: broadcast of rank 0's weights, per-rank batches, one gradient all-reduce per step.
+    The replicas' parameters must stay bit-identical (BatchNorm buffers are per-rank by design)."""
+    from vs_seg_b200.ddp import shard_list
+    out = str(tmp_path / "sd")
+    mp.spawn(_ddp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = torch.load(out + ".0"), torch.load(out + ".1")
+    for k in a:
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert torch.equal(a[k], b[k]), k
+    # shards: padded round-robin, every item covered, equal lengths
+    items = list(range(7))
+    shards = [shard_list(items, r, 3) for r in range(3)]
+    assert all(len(s) == 3 for s in shards) and set(sum(shards, [])) == set(items)
+    assert shard_list(items, 0, 1) == items

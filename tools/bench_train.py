@@ -51,7 +51,8 @@ def main():
     out = {"shape": list(shape), "steps": steps}
 
     net = make(dev)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=1e-7)
+    from vs_seg_b200.optim import FusedAdam
+    opt = FusedAdam(net.parameters(), lr=1e-4, weight_decay=1e-7)   # one fused launch over the flat parameter buffer
 
     def native_step():
         opt.zero_grad()
