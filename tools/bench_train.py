@@ -53,6 +53,8 @@ def main():
     net = make(dev)
     from vs_seg_b200.optim import FusedAdam
     opt = FusedAdam(net.parameters(), lr=1e-4, weight_decay=1e-7)   # one fused launch over the flat parameter buffer
+    if os.environ.get("VSSEG_BENCH_TORCH_ADAM"):
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, weight_decay=1e-7)
 
     def native_step():
         opt.zero_grad()
