@@ -479,6 +479,53 @@ def test_tcgen05_wgrad_matches_torch(B, cin, cout, dims, k):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,cin,cout,dims,transposed", [
+    (1, 16, 16, (8, 12, 128), False), (2, 32, 32, (4, 8, 128), False),      # downsample convs, stride (2,2,1)
+    (1, 32, 16, (4, 6, 128), True), (2, 48, 32, (2, 4, 128), True),         # upsample ConvTranspose3d, stride (2,2,1)
+])
+def test_tcgen05_wgrad_strided_and_transposed(B, cin, cout, dims, transposed):
+    """Weight gradient of the stride-(2,2,1) downsample / transposed upsample convs of levels 1-2 on the tensor-core
+    kernel (x and dc lines paired across the two grids) vs torch autograd and the CUDA-core kernel."""
+    import ctypes as C
+    from vs_seg_b200 import lib as vlib
+    from vs_seg_b200.tensors import Act8Buffer
+    dev = _dev()
+    lib = vlib.load()
+    k, stride = (3, 3, 1), (2, 2, 1)
+    g = torch.Generator().manual_seed(cin * 3 + cout)
+    x = torch.randn((B, cin) + dims, generator=g, dtype=torch.float64)
+    if transposed:
+        conv = torch.nn.ConvTranspose3d(cin, cout, k, stride=stride, padding=(1, 1, 0), output_padding=(1, 1, 0)).double()
+        odims = (dims[0] * 2, dims[1] * 2, dims[2])
+    else:
+        conv = torch.nn.Conv3d(cin, cout, k, stride=stride, padding=(1, 1, 0)).double()
+        odims = (dims[0] // 2, dims[1] // 2, dims[2])
+    dy = torch.randn((B, cout) + odims, generator=g, dtype=torch.float64)
+    out = conv(x)
+    assert tuple(out.shape[2:]) == odims
+    (out * dy).sum().backward()
+    ref = conv.weight.grad                                    # Conv3d [cout,cin,k] / ConvTranspose3d [cin,cout,k]
+    cpad = (cout + 15) // 16 * 16
+    xb = Act8Buffer(B, cin, *dims, dev).from_ncdhw(x.float().to(dev))
+    db = Act8Buffer(B, cout, *odims, dev).from_ncdhw(dy.float().to(dev))
+    geom = vlib.ConvGeom(*k, *stride, 1 if transposed else 0)
+    xv, dv = xb.view(), db.view()
+    assert lib.vsseg_conv3d_wgrad_tc_supported(C.byref(xv), C.byref(dv), C.byref(geom)) == 1
+    s = torch.cuda.current_stream(dev).cuda_stream
+    for tc in (True, False):
+        dw = torch.zeros((9, cin, cpad), device=dev)
+        if tc:
+            vlib.check(lib.vsseg_conv3d_wgrad_tc(C.byref(xv), C.byref(dv), C.byref(geom), dw.data_ptr(), cpad, s), "wgrad_tc")
+        else:
+            dbias = torch.zeros(cpad, device=dev)
+            vlib.check(lib.vsseg_conv3d_wgrad(C.byref(xv), C.byref(dv), C.byref(geom), dw.data_ptr(), cpad, dbias.data_ptr(), s),
+                       "wgrad")
+        got = dw[:, :, :cout].reshape(*k, cin, cout)
+        got = (got.permute(3, 4, 0, 1, 2) if transposed else got.permute(4, 3, 0, 1, 2)).cpu().double()
+        assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item(), ("tc" if tc else "cuda-core")
+
+
+@pytest.mark.gpu
 def test_fused_adam_matches_torch_adam():
     """vsseg_adam_step over the flat buffer vs torch.optim.Adam (reference VSparams.py:388-391 settings plus a
     larger weight decay, an lr change through param_groups as VSparams.py:517-523 does, odd tensor sizes)."""

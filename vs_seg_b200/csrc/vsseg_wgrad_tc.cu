@@ -17,6 +17,9 @@ struct WgArgs {
     float* dw;               // [taps][Cin][cout_pad]
     int cout_pad, KX, KY, KZ;
     int nslice;              // CTAs per (dx, dy) pair
+    // line pairing on the coarse (loop) grid XL x YL: x line = l * ax + (d - p) * bx, dc line = l * ad + (d - p) * bd.
+    // stride-1: (1,1,1,0); strided conv (x fine, dc coarse): (2,1,1,0); transposed conv (x coarse, dc fine): (1,0,2,1)
+    int ax, bx, ad, bd, XL, YL;
     int nstage;
     uint32_t dc_plane, x_plane, x_off, stage_bytes;   // bytes: dc plane size, x plane size, x region start
     uint32_t idesc;
@@ -40,7 +43,8 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
     const int slice = blockIdx.x % a.nslice, pair = blockIdx.x / a.nslice;
     const int dx = pair / a.KY, dy = pair % a.KY;
     const int px = (a.KX - 1) / 2, py = (a.KY - 1) / 2, hz = (a.KZ - 1) / 2;
-    const int X = a.dc.X, Y = a.dc.Y, Z = a.dc.Z;
+    const int X = a.XL, Y = a.YL, Z = a.dc.Z;      // loop grid (the coarser of the two tensors)
+    const int Xx = a.x.X, Yx = a.x.Y, Xd = a.dc.X, Yd = a.dc.Y;
     const int nzt = Z / 128;
     const int nlines = a.dc.B * X * Y * nzt;
     const int pitch = 128 + 2 * hz;
@@ -75,8 +79,9 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
             const int y = t % Y; t /= Y;
             const int xx = t % X; t /= X;
             const int b = t;
-            const int xi = xx + dx - px, yi = y + dy - py;
-            if (xi < 0 || xi >= X || yi < 0 || yi >= Y) continue;   // padding line: contributes nothing
+            const int xi = xx * a.ax + (dx - px) * a.bx, yi = y * a.ax + (dy - py) * a.bx;
+            const int xd = xx * a.ad + (dx - px) * a.bd, yd = y * a.ad + (dy - py) * a.bd;
+            if (xi < 0 || xi >= Xx || yi < 0 || yi >= Yx || xd < 0 || xd >= Xd || yd < 0 || yd >= Yd) continue;   // padding line
             const int st = it % a.nstage;
             mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
             const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
@@ -88,19 +93,19 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
             const bool zl = nzt > 1 && hz > 0 && z0 - hz < 0, zh = nzt > 1 && hz > 0 && z0 + 128 + hz > Z;
             if (lane == 0)
                 mbar_expect_tx(full + st, (uint32_t)ndc * 2048u + (uint32_t)nx * (xrow + (zl ? 16u : 0u) + (zh ? 16u : 0u)));
-            const int64_t nvox = (int64_t)X * Y * Z;
+            const int64_t nvox_d = (int64_t)Xd * Yd * Z, nvox_x = (int64_t)Xx * Yx * Z;
             for (int q = lane; q < ndc + nx; q += 32) {
                 if (q < ndc) {
                     const int plane = q & 1, cg = q >> 1;
                     const __nv_bfloat16* gp = (const __nv_bfloat16*)a.dc.hi + (int64_t)plane * a.dc.lo_offset +
                                               (int64_t)b * a.dc.batch_stride +
-                                              ((int64_t)cg * nvox + ((int64_t)xx * Y + y) * Z + z0) * 8;
+                                              ((int64_t)cg * nvox_d + ((int64_t)xd * Yd + yd) * Z + z0) * 8;
                     bulk_load(base + (uint32_t)plane * a.dc_plane + (uint32_t)cg * 2048u, gp, 2048u, full + st);
                 } else {
                     const int r = q - ndc, plane = r & 1, cg = r >> 1;
                     const __nv_bfloat16* gp = (const __nv_bfloat16*)a.x.hi + (int64_t)plane * a.x.lo_offset +
                                               (int64_t)b * a.x.batch_stride +
-                                              ((int64_t)cg * nvox + ((int64_t)xi * Y + yi) * Z + zlo) * 8;
+                                              ((int64_t)cg * nvox_x + ((int64_t)xi * Yx + yi) * Z + zlo) * 8;
                     const uint32_t line = base + a.x_off + (uint32_t)plane * a.x_plane + (uint32_t)(cg * pitch) * 16;
                     bulk_load(line + (uint32_t)(zlo - (z0 - hz)) * 16, gp, xrow, full + st);
                     if (zl) bulk_load(line, g_zero_line_wg, 16, full + st);
@@ -119,8 +124,9 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
                 int t = ln / nzt;
                 const int y = t % Y; t /= Y;
                 const int xx = t % X;
-                const int xi = xx + dx - px, yi = y + dy - py;
-                if (xi < 0 || xi >= X || yi < 0 || yi >= Y) continue;
+                const int xi = xx * a.ax + (dx - px) * a.bx, yi = y * a.ax + (dy - py) * a.bx;
+                const int xd = xx * a.ad + (dx - px) * a.bd, yd = y * a.ad + (dy - py) * a.bd;
+                if (xi < 0 || xi >= Xx || yi < 0 || yi >= Yx || xd < 0 || xd >= Xd || yd < 0 || yd >= Yd) continue;
                 const int st = it % a.nstage;
                 mbar_wait(full + st, (it / a.nstage) & 1);
                 tc_fence_after();
@@ -158,8 +164,9 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
             int t = ln / nzt;
             const int y = t % Y; t /= Y;
             const int xx = t % X;
-            const int xi = xx + dx - px, yi = y + dy - py;
-            any = !(xi < 0 || xi >= X || yi < 0 || yi >= Y);
+            const int xi = xx * a.ax + (dx - px) * a.bx, yi = y * a.ax + (dy - py) * a.bx;
+            const int xd = xx * a.ad + (dx - px) * a.bd, yd = y * a.ad + (dy - py) * a.bd;
+            any = !(xi < 0 || xi >= Xx || yi < 0 || yi >= Yx || xd < 0 || xd >= Xd || yd < 0 || yd >= Yd);
         }
         if (any) {
             for (int dz = 0; dz < a.KZ; ++dz) {
@@ -189,9 +196,14 @@ using namespace vsseg;
 extern "C" {
 
 int vsseg_conv3d_wgrad_tc_supported(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_conv_geom* g) {
-    if (!x || !dc || !g || g->transposed || g->sx != 1 || g->sy != 1 || g->sz != 1) return 0;
+    if (!x || !dc || !g || g->sz != 1 || g->sx != g->sy || g->sx < 1 || g->sx > 2) return 0;
     if ((g->kx != 1 && g->kx != 3) || (g->ky != 1 && g->ky != 3) || (g->kz != 1 && g->kz != 3)) return 0;
-    if (x->X != dc->X || x->Y != dc->Y || x->Z != dc->Z || x->B != dc->B) return 0;
+    if (g->sx == 2 && (g->kx != 3 || g->ky != 3)) return 0;
+    if (g->transposed && g->sx != 2) return 0;
+    // x = the conv's input, dc = gradient of its output: equal extents (stride 1), x twice dc (strided conv),
+    // dc twice x (transposed conv: output_padding makes the output exactly 2x); z is never strided here
+    const int fx = g->transposed ? 1 : g->sx, fd = g->transposed ? g->sx : 1;
+    if (x->X * fd != dc->X * fx || x->Y * fd != dc->Y * fx || x->Z != dc->Z || x->B != dc->B) return 0;
     if (x->Z % 128 || x->C % 16 || dc->C % 8 || dc->C > 128 || x->C > 256) return 0;
     if (g->kz * x->C > 512) return 0;
     return 1;
@@ -204,6 +216,9 @@ int vsseg_conv3d_wgrad_tc(const vsseg_act8* x, const vsseg_act8* dc, const vsseg
     WgArgs a{};
     a.x = *x; a.dc = *dc; a.dw = dw; a.cout_pad = cout_pad;
     a.KX = g->kx; a.KY = g->ky; a.KZ = g->kz;
+    if (g->transposed) { a.ax = 1; a.bx = 0; a.ad = 2; a.bd = 1; a.XL = x->X; a.YL = x->Y; }
+    else if (g->sx == 2) { a.ax = 2; a.bx = 1; a.ad = 1; a.bd = 0; a.XL = dc->X; a.YL = dc->Y; }
+    else { a.ax = 1; a.bx = 1; a.ad = 1; a.bd = 0; a.XL = dc->X; a.YL = dc->Y; }
     const int hz = (g->kz - 1) / 2, pitch = 128 + 2 * hz;
     // M = 128 always: the A rows beyond Cout read whatever follows the dc plane in shared memory; a row of A only
     // feeds its own row of D, and those TMEM lanes are never read
@@ -224,7 +239,7 @@ int vsseg_conv3d_wgrad_tc(const vsseg_act8* x, const vsseg_act8* dc, const vsseg
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long nlines = (long)dc->B * dc->X * dc->Y * (dc->Z / 128);
+    const long nlines = (long)dc->B * a.XL * a.YL * (dc->Z / 128);
     long ns = sms / pairs;
     if (ns < 1) ns = 1;
     if (ns > nlines) ns = nlines;
