@@ -134,6 +134,12 @@ int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const
 int vsseg_conv3d_tc_f32out_2p(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g,
                               const void* w_packed, const vsseg_epilogue* ep, const float* sw_weight, void* stream);
 
+/* Attention conv2 + Sigmoid (two-pass weight image, Cout = 1) with AttentionBlock2 fused into its epilogue
+ * (reference attentionblock.py:21-47): the map is stored to `att` and every channel of `gated` (the tensor
+ * the block gates, same extents) is scaled in place by 1 + att.  One launch instead of conv2 + vsseg_att_gate. */
+int vsseg_conv3d_tc_attgate(const vsseg_act8* in, const vsseg_f32view* att, const vsseg_conv_geom* g,
+                            const void* w_packed, const vsseg_epilogue* ep, const vsseg_act8* gated, void* stream);
+
 /* Human-readable description of the launch plan (tile, stages, op table) for tests and DESIGN.md. */
 int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
                              int32_t n_split, const vsseg_act8* shortcut_src, char* buf, int32_t buflen);

@@ -64,6 +64,11 @@ __device__ __forceinline__ uint4 ldg128(const void* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
+// plain (coherent) 128-bit load for data this kernel also writes
+__device__ __forceinline__ uint4 ldg128_plain(const void* p) {
+    return *reinterpret_cast<const uint4*>(p);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == 1) return 1.0f / (1.0f + expf(-v));
     return v >= 0.f ? v : v * slope;

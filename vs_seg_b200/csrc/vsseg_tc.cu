@@ -103,6 +103,7 @@ struct TcArgs {
     TcEl el2[TC_MAX_OPS2 / 3];
     uint32_t desc_hi;          // upper descriptor word (SBO = 128 B, version 1)
     int partial;               // the last y line group is partial (rows beyond Ym are masked)
+    vsseg_act8 gate;           // out mode 2: AttentionBlock2 gate applied in place to this tensor, x *= 1 + att
     int two_pass;              // Cout <= 2 planar output: weights packed [hi | lo] along N, two MMAs per product
 };
 
@@ -188,7 +189,7 @@ __device__ __forceinline__ void epi_load(const EpiCtx& X, EpiUnit<SC, RM>& U) {
     U.valid = !a.partial || X.my0 + X.ly + a.accs[U.ai].yl < a.Ym;
     U.rsrc = 0.f;
     U.oy = U.oz = 0;
-    if constexpr (RM == 2 || OM == 1) {
+    if constexpr (RM == 2 || OM >= 1) {
         U.oy = (X.my0 + X.ly) * a.uy + a.accs[U.ai].y_add;
         U.oz = (X.mz0 + X.zz) * a.uz + a.accs[U.ai].z_add;
     }
@@ -214,7 +215,7 @@ __device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) 
     if (!U.live || !U.valid || (a.dbgf & 1)) return;
     const int c0 = U.c << 4;
     const float* ep_c = X.ep_c;
-    if constexpr (OM == 1) {
+    if constexpr (OM >= 1) {
         // planar fp32 output: attention map (sigmoid) or logits, optionally blended into the
         // sliding-window accumulator (MONAI sliding_window_inference step 6)
         const int Yo = a.out.Y, Zo = a.out.Z;
@@ -229,6 +230,29 @@ __device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) 
             float* o = a.outf.ptr + X.b * a.outf.sb + q * a.outf.sc + X.ox * a.outf.sx + U.oy * a.outf.sy + U.oz * a.outf.sz;
             if (a.sw_weight) *o += sw * f;
             else *o = f;
+            if constexpr (OM == 2) {
+                // AttentionBlock2 (reference attentionblock.py:39-47) fused into the conv that produces the map:
+                // every channel group of this voxel is scaled by 1 + att in place (split-bf16 -> fp32 -> split-bf16)
+                if (q == 0) {
+                    const float gsc = 1.0f + f;
+                    const int Xg = a.gate.X, Yg = a.gate.Y, Zg = a.gate.Z;
+                    const int64_t cgs_g = (int64_t)Xg * Yg * Zg * 8;
+                    __nv_bfloat16* gp = (__nv_bfloat16*)a.gate.hi + (int64_t)X.b * a.gate.batch_stride +
+                                        (((int64_t)X.ox * Yg + U.oy) * Zg + U.oz) * 8;
+                    const int ncg = a.gate.C >> 3;
+#pragma unroll 2
+                    for (int cg = 0; cg < ncg; ++cg, gp += cgs_g) {
+                        float xv[8];
+                        unpack8(ldg128_plain(gp), ldg128_plain(gp + a.gate.lo_offset), xv);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) xv[k] *= gsc;
+                        uint4 h, l;
+                        pack8(xv, h, l);
+                        *reinterpret_cast<uint4*>(gp) = h;
+                        *reinterpret_cast<uint4*>(gp + a.gate.lo_offset) = l;
+                    }
+                }
+            }
         }
         return;
     } else {
@@ -333,7 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
     if (warp == 1) tmem_alloc(tmem_ptr, a.tmem_cols);
     {
-        const int ncp = (a.out_mode == 1 ? 16 : (a.cout + 15) / 16 * 16);   // all n-slices (<= 256 channels)
+        const int ncp = (a.out_mode >= 1 ? 16 : (a.cout + 15) / 16 * 16);   // all n-slices (<= 256 channels)
         for (int i = threadIdx.x; i < ncp; i += TC_THREADS) {
             ep_c[i] = a.ep.scale[i];
             ep_c[256 + i] = a.ep.shift[i];
@@ -1096,6 +1120,7 @@ static int encode_map(CUtensorMap* tmap, const vsseg_act8* t, int cg_plane, int 
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcArgs);
 static TcKernel pick_kernel(const TcArgs& a) {
     const bool sc = a.nchunk2 != 0;
+    if (a.out_mode == 2) return conv_tc_kernel<2, false, 0>;
     if (a.out_mode == 1) return conv_tc_kernel<1, false, 0>;
     if (sc) return a.res_mode == 0 ? conv_tc_kernel<0, true, 0> : a.res_mode == 1 ? conv_tc_kernel<0, true, 1> : conv_tc_kernel<0, true, 2>;
     return a.res_mode == 0 ? conv_tc_kernel<0, false, 0> : a.res_mode == 1 ? conv_tc_kernel<0, false, 1> : conv_tc_kernel<0, false, 2>;
@@ -1103,7 +1128,7 @@ static TcKernel pick_kernel(const TcArgs& a) {
 static int set_smem_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        const TcKernel all[] = {conv_tc_kernel<1, false, 0>, conv_tc_kernel<0, true, 0>, conv_tc_kernel<0, true, 1>, conv_tc_kernel<0, true, 2>,
+        const TcKernel all[] = {conv_tc_kernel<2, false, 0>, conv_tc_kernel<1, false, 0>, conv_tc_kernel<0, true, 0>, conv_tc_kernel<0, true, 1>, conv_tc_kernel<0, true, 2>,
                                 conv_tc_kernel<0, false, 0>, conv_tc_kernel<0, false, 1>, conv_tc_kernel<0, false, 2>};
         for (TcKernel k : all) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1179,7 +1204,7 @@ int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, c
 }
 
 static int tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
-                     const vsseg_epilogue* ep, const float* sw_weight, void* stream, int two_pass) {
+                     const vsseg_epilogue* ep, const float* sw_weight, void* stream, int two_pass, const vsseg_act8* gate = nullptr) {
     VSSEG_REQUIRE(in && out && out->ptr && out->C >= 1 && out->C <= 2, "conv3d_tc_f32out: Cout must be 1 or 2");
     // the plan only needs the output extents: describe the planar output as a 16-channel act8 tensor
     vsseg_act8 o16{};
@@ -1192,6 +1217,12 @@ static int tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg
     a.ep = *ep;
     a.w = (const uint8_t*)w_packed;
     a.out_mode = 1;
+    if (gate) {
+        VSSEG_REQUIRE(gate->hi && gate->C % 8 == 0 && gate->B == out->B && gate->X == out->X && gate->Y == out->Y && gate->Z == out->Z &&
+                          out->C == 1 && !sw_weight, "conv3d_tc_attgate: the gated tensor must have the map's extents (Cout = 1)");
+        a.out_mode = 2;
+        a.gate = *gate;
+    }
     a.outf = *out;
     a.cout = out->C;
     a.two_pass = two_pass;
@@ -1212,6 +1243,12 @@ int vsseg_conv3d_tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const
 int vsseg_conv3d_tc_f32out_2p(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
                               const vsseg_epilogue* ep, const float* sw_weight, void* stream) {
     return tc_f32out(in, out, g, w_packed, ep, sw_weight, stream, 1);
+}
+
+int vsseg_conv3d_tc_attgate(const vsseg_act8* in, const vsseg_f32view* att, const vsseg_conv_geom* g, const void* w_packed,
+                            const vsseg_epilogue* ep, const vsseg_act8* gated, void* stream) {
+    VSSEG_REQUIRE(gated, "conv3d_tc_attgate: NULL gated tensor");
+    return tc_f32out(in, att, g, w_packed, ep, nullptr, stream, 1, gated);
 }
 
 int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int32_t n_split,

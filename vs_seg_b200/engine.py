@@ -18,6 +18,7 @@ of fused kernel launches through the C ABI:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import torch
@@ -282,9 +283,11 @@ class UNetEvalPlan:
         pad = [0, 0] * (w.dim() - 1 - d) + [0, c - w.shape[d]]
         return torch.nn.functional.pad(w, pad)
 
-    def _add_smallcout(self, name, src, out_view, k, w, bias, act_code, slope, sw_weight=None, nb_extra=0):
+    def _add_smallcout(self, name, src, out_view, k, w, bias, act_code, slope, sw_weight=None, nb_extra=0, gate=None):
         """Conv with 1-2 output channels -> planar fp32: tensor-core path when the shape is covered
-        (weights zero-padded to Cin = src.C, Cout = 16), else the CUDA-core kernel."""
+        (weights zero-padded to Cin = src.C, Cout = 16), else the CUDA-core kernel.
+        gate: act8 view that AttentionBlock2 scales by 1 + out (Cout = 1); returns True when the gate was fused
+        into this launch (tensor-core path), else the caller adds the gate launch."""
         g = self._geom(k)
         cout = w.shape[0]
         fl, nb = _conv_cost(src, src, k, False, src.C, cout)  # stride 1: output extents = input extents
@@ -300,15 +303,28 @@ class UNetEvalPlan:
                 shift = self._dev(torch.nn.functional.pad(bias.float(), (0, 16 - cout)))
                 ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, act_code)
                 self._keep.append(ep)
+                # measured (group of 8 windows): the fused gate wins where the gated tensor is small enough for its
+                # traffic to hide behind the MMAs (level 3 and coarser: -9 us per window at 32x32x128); on the two
+                # finest levels the gate is the larger half and runs faster as its own bandwidth-bound launch
+                fuse_env = os.environ.get("VSSEG_FUSE_GATE", "auto")
+                fuse = fuse_env == "1" or (fuse_env == "auto" and gate is not None and _nvox(gate) // gate.B <= 32 * 32 * 128)
+                if gate is not None and cout == 1 and sw_weight is None and fuse:
+                    self._keep.append(gate)
+                    self.steps.append(_Step(name + "+gate", self.lib.vsseg_conv3d_tc_attgate,
+                                            (C.byref(src), C.byref(out_view), C.byref(g), wp.data_ptr(), C.byref(ep),
+                                             C.byref(gate)), fl + 2 * _nvox(gate) * gate.C,
+                                            nb + 8 * _nvox(gate) * gate.C, kind="tcgen05"))
+                    return True
                 self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc_f32out_2p,
                                         (C.byref(src), C.byref(out_view), C.byref(g), wp.data_ptr(), C.byref(ep),
                                          sw_weight), fl, nb, kind="tcgen05"))
-                return
+                return False
         wg = self._dev(pack_conv_weight(w, False))
         b = self._dev(bias.float())
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_smallcout,
                                 (C.byref(src), C.byref(out_view), C.byref(g), wg.data_ptr(), b.data_ptr(), act_code,
                                  slope, sw_weight), fl, nb))
+        return False
 
     def _add_shortcut(self, name, p, src, dst):
         """1x1x1 shortcut conv of a ResidualUnit (convolutions.py:241-250) -> addend buffer."""
@@ -336,10 +352,11 @@ class UNetEvalPlan:
             att = self._att[key] = torch.empty((self.B, 1, buf.X, buf.Y, buf.Z), dtype=torch.float32, device=self.device)
             self.att_maps.append(att)
         av = f32view(att[self._bs[0]:self._bs[0] + self._bs[1]])
-        self._add_smallcout(name + ".conv2", h, av, k, self.sd[p + "0.conv2.conv.weight"],
-                            self.sd[p + "0.conv2.conv.bias"], 1, 0.0)
-        self.steps.append(_Step(name + ".gate", self.lib.vsseg_att_gate, (C.byref(src), C.byref(av), C.byref(src)),
-                                2 * _nvox(src) * cin, 4 * _nvox(src) * (2 * cin + 1)))
+        fused = self._add_smallcout(name + ".conv2", h, av, k, self.sd[p + "0.conv2.conv.weight"],
+                                    self.sd[p + "0.conv2.conv.bias"], 1, 0.0, gate=src)
+        if not fused:
+            self.steps.append(_Step(name + ".gate", self.lib.vsseg_att_gate, (C.byref(src), C.byref(av), C.byref(src)),
+                                    2 * _nvox(src) * cin, 4 * _nvox(src) * (2 * cin + 1)))
         self._keep += [src, h, av]
 
     def _add_ru(self, name, p, src, h_buf, r_buf, dst, k, subunits):

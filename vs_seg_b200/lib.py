@@ -52,6 +52,7 @@ _SIGNATURES = {
                                          C.c_void_p]),
     "vsseg_conv3d_tc_f32out_2p": (C.c_int, [_P(Act8), _P(F32View), _P(ConvGeom), C.c_void_p, _P(Epilogue), C.c_void_p,
                                             C.c_void_p]),
+    "vsseg_conv3d_tc_attgate": (C.c_int, [_P(Act8), _P(F32View), _P(ConvGeom), C.c_void_p, _P(Epilogue), _P(Act8), C.c_void_p]),
     "vsseg_conv3d_tc_describe": (C.c_int, [_P(Act8), _P(Act8), _P(ConvGeom), C.c_int32, _P(Act8), C.c_char_p, C.c_int32]),
     "vsseg_conv3d_tc": (C.c_int, [_P(Act8), _P(Act8), _P(ConvGeom), C.c_void_p, C.c_int32, _P(Epilogue),
                                   _P(Act8), _P(F32View), C.c_void_p, C.c_void_p,
