@@ -156,6 +156,11 @@ def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="c
         # reads its input in place and blends its logits straight into the accumulator.
         group = max(1, int(os.environ.get("VSSEG_SW_GROUP", "8")))
         levels = int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"))
+        # a group plan keeps every activation of its windows resident (~400 B per window voxel): keep it
+        # within a quarter of the free device memory (large roi sizes, e.g. the reference's 384x384x64)
+        free_b, _ = torch.cuda.mem_get_info(inputs.device)
+        per_window = 400 * roi_size[0] * roi_size[1] * roi_size[2]
+        group = max(1, min(group, int(0.25 * free_b // per_window)))
         acc = torch.zeros((batch, model.out_channels) + image_size, dtype=torch.float32, device=inputs.device)
         wptr = imap.data_ptr()
         for g0 in range(0, len(jobs), group):
