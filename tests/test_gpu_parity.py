@@ -395,7 +395,8 @@ def _train_pair(attention, seed=0):
     return ref.train(), nat.to(_dev()).train()
 
 
-@pytest.mark.parametrize("attention,shape", [(True, (2, 1, 64, 64, 16)), (False, (1, 1, 64, 32, 16))])
+@pytest.mark.parametrize("attention,shape", [(True, (2, 1, 64, 64, 16)), (False, (1, 1, 64, 32, 16)),
+                                             (True, (1, 1, 32, 32, 32))])   # Z >= 32: line-structured small-Cout wgrad
 def test_unet_train_step_matches_torch_autograd(attention, shape):
     """Train-mode forward (batch-stat BatchNorm), Dice_spvPA loss and every parameter gradient of the native path
     vs the torch containers + autograd on the CPU (dropout 0: masks cannot be matched bit for bit)."""

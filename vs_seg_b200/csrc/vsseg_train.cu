@@ -544,6 +544,89 @@ __global__ void __launch_bounds__(128) smallcout_wgrad_kernel(const SmallBwdArgs
     }
 }
 
+// Line-structured version for Z >= 32: a block owns one channel group, one z tap and a slab of (b, x, y) lines; its
+// threads walk z, so all index arithmetic is per line (the kernel above spends ~100 instructions of 64-bit div/mod per
+// voxel and re-reads dy for every (tap, channel group): 2.3 ms for the logits conv of a 2 x 128^3 batch).  A thread keeps
+// the KX*KY (dx, dy) taps of its 8 channels in registers and loads dy (and the sigmoid output) once per voxel.
+template <int COUT, int KXY>
+__global__ void __launch_bounds__(128) smallcout_wgrad_lines_kernel(const SmallBwdArgs a, int lines_per_block) {
+    constexpr int KX = KXY == 9 ? 3 : 1, KY = KX;
+    const int cg = blockIdx.z, tz = blockIdx.y, C = a.x.C;
+    const int X = a.x.X, Y = a.x.Y, Z = a.x.Z;
+    const int pz = (a.g.kz - 1) / 2;
+    const int64_t nvox = (int64_t)X * Y * Z;
+    const int nlines = a.x.B * X * Y;
+    float acc[KXY][8][COUT], bs[COUT];
+#pragma unroll
+    for (int t = 0; t < KXY; ++t)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[t][k][co] = 0.f;
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) bs[co] = 0.f;
+    const bool do_bias = tz == 0 && cg == 0;
+    const int l0 = blockIdx.x * lines_per_block, l1 = min(l0 + lines_per_block, nlines);
+    for (int ln = l0; ln < l1; ++ln) {
+        const int y = ln % Y, x = (ln / Y) % X, b = ln / (Y * X);     // per line, block-uniform
+        const float* dyp = a.dy.ptr + b * a.dy.sb + x * a.dy.sx + y * a.dy.sy;
+        const float* yp = a.y.ptr + b * a.y.sb + x * a.y.sx + y * a.y.sy;
+        for (int z = threadIdx.x; z < Z; z += 128) {
+            float d[COUT];
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                d[co] = __ldg(dyp + co * a.dy.sc + z * a.dy.sz);
+                if (a.sigmoid) {
+                    const float sg = __ldg(yp + co * a.y.sc + z * a.y.sz);
+                    d[co] *= sg * (1.f - sg);
+                }
+                bs[co] += d[co];
+            }
+            const int zi = z - pz + tz;
+            if (zi < 0 || zi >= Z) continue;
+#pragma unroll
+            for (int tx = 0; tx < KX; ++tx)
+#pragma unroll
+                for (int ty = 0; ty < KY; ++ty) {
+                    const int xi = x - (KX - 1) / 2 + tx, yi = y - (KY - 1) / 2 + ty;
+                    if (xi < 0 || xi >= X || yi < 0 || yi >= Y) continue;     // block-uniform
+                    float f[8];
+                    g8_load(a.x, b, cg, ((int64_t)xi * Y + yi) * Z + zi, nvox, f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int co = 0; co < COUT; ++co) acc[tx * KY + ty][k][co] = fmaf(f[k], d[co], acc[tx * KY + ty][k][co]);
+                }
+        }
+    }
+    // block reduction: warp shuffle, then one atomic per (tap, channel, cout) and block
+    __shared__ float red[4][KXY * 8 * COUT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < KXY; ++t)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float sum = warp_sum_f(acc[t][k][co]);
+                if (lane == 0) red[warp][(t * 8 + k) * COUT + co] = sum;
+            }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KXY * 8 * COUT; i += 128) {
+        const float sum = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+        const int co = i % COUT, k = (i / COUT) % 8, t = i / (8 * COUT);
+        const int tap = t * a.g.kz + tz;      // tap = (tx * KY + ty) * KZ + tz
+        atomicAdd(a.dw + ((int64_t)tap * C + cg * 8 + k) * COUT + co, sum);
+    }
+    if (do_bias) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            const float sum = warp_sum_f(bs[co]);
+            if (lane == 0) atomicAdd(a.dbias + co, sum);
+        }
+    }
+}
+
 // ---- attention gate backward: g = x*(1+att)  =>  dx = dg*(1+att) [+ dx], datt = sum_c dg_c * x_c ------------
 __global__ void __launch_bounds__(256) gate_bwd_kernel(vsseg_act8 x, vsseg_f32view att, vsseg_act8 dg, vsseg_act8 dx,
                                                        vsseg_f32view datt, int accumulate) {
@@ -708,6 +791,18 @@ int vsseg_conv3d_smallcout_bwd(const vsseg_act8* x, const vsseg_f32view* dy, con
     }
     if (dw) {
         VSSEG_REQUIRE(dbias, "smallcout_bwd: dw without dbias");
+        const int kxy = g->kx * g->ky;
+        if (x->Z >= 32 && g->kx == g->ky && (kxy == 9 || kxy == 1)) {
+            const int nlines = x->B * x->X * x->Y;
+            int lpb = (nlines + 592 - 1) / 592;     // ~4 blocks per SM and (z tap, channel group)
+            if (lpb < 1) lpb = 1;
+            dim3 grid((unsigned)((nlines + lpb - 1) / lpb), (unsigned)g->kz, (unsigned)(x->C / 8));
+            if (dy->C == 1 && kxy == 9) smallcout_wgrad_lines_kernel<1, 9><<<grid, 128, 0, s>>>(a, lpb);
+            else if (dy->C == 1) smallcout_wgrad_lines_kernel<1, 1><<<grid, 128, 0, s>>>(a, lpb);
+            else if (kxy == 9) smallcout_wgrad_lines_kernel<2, 9><<<grid, 128, 0, s>>>(a, lpb);
+            else smallcout_wgrad_lines_kernel<2, 1><<<grid, 128, 0, s>>>(a, lpb);
+            return check_launch("smallcout_wgrad_lines");
+        }
         dim3 grid(ew_grid(nvox, 128 * 32), (unsigned)taps, (unsigned)(x->C / 8));
         if (dy->C == 1) smallcout_wgrad_kernel<1><<<grid, 128, 0, s>>>(a);
         else smallcout_wgrad_kernel<2><<<grid, 128, 0, s>>>(a);
