@@ -442,6 +442,7 @@ def test_unet_train_step_matches_torch_autograd(attention, shape):
 @pytest.mark.parametrize("B,cin,cout,dims,k", [
     (1, 16, 16, (4, 6, 128), (3, 3, 1)), (2, 32, 48, (3, 4, 128), (3, 3, 3)), (1, 96, 48, (2, 3, 128), (3, 3, 3)),
     (1, 64, 32, (4, 4, 256), (3, 3, 1)), (1, 16, 32, (4, 4, 128), (1, 1, 1)), (1, 48, 40, (3, 3, 128), (3, 3, 3)),
+    (1, 64, 64, (4, 4, 64), (3, 3, 3)), (2, 160, 80, (2, 3, 32), (3, 3, 3)), (1, 128, 64, (3, 4, 64), (1, 1, 1)),   # coarse levels: whole-Z lines
 ])
 def test_tcgen05_wgrad_matches_torch(B, cin, cout, dims, k):
     """Tensor-core weight gradient (MN-major operands, split-K atomics) vs torch.nn.grad on the CPU, and vs the

@@ -20,6 +20,7 @@ struct WgArgs {
     // line pairing on the coarse (loop) grid XL x YL: x line = l * ax + (d - p) * bx, dc line = l * ad + (d - p) * bd.
     // stride-1: (1,1,1,0); strided conv (x fine, dc coarse): (2,1,1,0); transposed conv (x coarse, dc fine): (1,0,2,1)
     int ax, bx, ad, bd, XL, YL;
+    int LZ;                  // z extent of a staged line: 128, or the whole Z (32 / 64) on the coarse levels
     int nstage;
     uint32_t dc_plane, x_plane, x_off, stage_bytes;   // bytes: dc plane size, x plane size, x region start
     uint32_t idesc;
@@ -45,9 +46,10 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
     const int px = (a.KX - 1) / 2, py = (a.KY - 1) / 2, hz = (a.KZ - 1) / 2;
     const int X = a.XL, Y = a.YL, Z = a.dc.Z;      // loop grid (the coarser of the two tensors)
     const int Xx = a.x.X, Yx = a.x.Y, Xd = a.dc.X, Yd = a.dc.Y;
-    const int nzt = Z / 128;
+    const int LZ = a.LZ;
+    const int nzt = Z / LZ;
     const int nlines = a.dc.B * X * Y * nzt;
-    const int pitch = 128 + 2 * hz;
+    const int pitch = LZ + 2 * hz;
     const int Cin = a.x.C, Cout = a.dc.C;
 
     if (threadIdx.x == 0) {
@@ -85,14 +87,14 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
             const int st = it % a.nstage;
             mbar_wait(empty + st, ((it / a.nstage) & 1) ^ 1);
             const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-            const int z0 = zt * 128;
-            const int zlo = max(z0 - hz, 0), zhi = min(z0 + 128 + hz, Z);
+            const int z0 = zt * LZ;
+            const int zlo = max(z0 - hz, 0), zhi = min(z0 + LZ + hz, Z);
             const uint32_t xrow = (uint32_t)(zhi - zlo) * 16;
             const int ndc = (Cout / 8) * 2, nx = (Cin / 8) * 2;
             // several z tiles: halo rows of an interior tile carry data, of a border tile must be re-zeroed
-            const bool zl = nzt > 1 && hz > 0 && z0 - hz < 0, zh = nzt > 1 && hz > 0 && z0 + 128 + hz > Z;
+            const bool zl = nzt > 1 && hz > 0 && z0 - hz < 0, zh = nzt > 1 && hz > 0 && z0 + LZ + hz > Z;
             if (lane == 0)
-                mbar_expect_tx(full + st, (uint32_t)ndc * 2048u + (uint32_t)nx * (xrow + (zl ? 16u : 0u) + (zh ? 16u : 0u)));
+                mbar_expect_tx(full + st, (uint32_t)ndc * (uint32_t)(LZ * 16) + (uint32_t)nx * (xrow + (zl ? 16u : 0u) + (zh ? 16u : 0u)));
             const int64_t nvox_d = (int64_t)Xd * Yd * Z, nvox_x = (int64_t)Xx * Yx * Z;
             for (int q = lane; q < ndc + nx; q += 32) {
                 if (q < ndc) {
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
                     const __nv_bfloat16* gp = (const __nv_bfloat16*)a.dc.hi + (int64_t)plane * a.dc.lo_offset +
                                               (int64_t)b * a.dc.batch_stride +
                                               ((int64_t)cg * nvox_d + ((int64_t)xd * Yd + yd) * Z + z0) * 8;
-                    bulk_load(base + (uint32_t)plane * a.dc_plane + (uint32_t)cg * 2048u, gp, 2048u, full + st);
+                    bulk_load(base + (uint32_t)plane * a.dc_plane + (uint32_t)(cg * LZ * 16), gp, (uint32_t)(LZ * 16), full + st);
                 } else {
                     const int r = q - ndc, plane = r & 1, cg = r >> 1;
                     const __nv_bfloat16* gp = (const __nv_bfloat16*)a.x.hi + (int64_t)plane * a.x.lo_offset +
@@ -132,14 +134,14 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_tc_kernel(const __grid_
                 tc_fence_after();
                 const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
                 // MN-major, no swizzle: SBO = stride between 8-channel groups, LBO = stride between 8-row K blocks
-                const uint64_t da_h = make_desc(base, 128, 2048);
-                const uint64_t da_l = make_desc(base + a.dc_plane, 128, 2048);
+                const uint64_t da_h = make_desc(base, 128, (uint32_t)(LZ * 16));
+                const uint64_t da_l = make_desc(base + a.dc_plane, 128, (uint32_t)(LZ * 16));
                 const uint64_t db_h = make_desc(base + a.x_off, 128, (uint32_t)pitch * 16);
                 const uint64_t db_l = make_desc(base + a.x_off + a.x_plane, 128, (uint32_t)pitch * 16);
                 for (int dz = 0; dz < a.KZ; ++dz) {
                     const uint32_t d = tmem_base + (uint32_t)(dz * Cin);
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll 4
+                    for (int ks = 0; ks < (LZ >> 4); ++ks) {
                         const uint64_t ka = (uint64_t)(ks * 16), kb = (uint64_t)(ks * 16 + dz);   // 16 B units: 16 rows per K step
                         umma_bf16(d, da_h + ka, db_h + kb, a.idesc, (first && ks == 0) ? 0u : 1u);
                         umma_bf16(d, da_l + ka, db_h + kb, a.idesc, 1u);
@@ -204,7 +206,7 @@ int vsseg_conv3d_wgrad_tc_supported(const vsseg_act8* x, const vsseg_act8* dc, c
     // dc twice x (transposed conv: output_padding makes the output exactly 2x); z is never strided here
     const int fx = g->transposed ? 1 : g->sx, fd = g->transposed ? g->sx : 1;
     if (x->X * fd != dc->X * fx || x->Y * fd != dc->Y * fx || x->Z != dc->Z || x->B != dc->B) return 0;
-    if (x->Z % 128 || x->C % 16 || dc->C % 8 || dc->C > 128 || x->C > 256) return 0;
+    if ((x->Z % 128 && x->Z != 64 && x->Z != 32) || x->C % 16 || dc->C % 8 || dc->C > 128 || x->C > 256) return 0;
     if (g->kz * x->C > 512) return 0;
     return 1;
 }
@@ -219,10 +221,11 @@ int vsseg_conv3d_wgrad_tc(const vsseg_act8* x, const vsseg_act8* dc, const vsseg
     if (g->transposed) { a.ax = 1; a.bx = 0; a.ad = 2; a.bd = 1; a.XL = x->X; a.YL = x->Y; }
     else if (g->sx == 2) { a.ax = 2; a.bx = 1; a.ad = 1; a.bd = 0; a.XL = dc->X; a.YL = dc->Y; }
     else { a.ax = 1; a.bx = 1; a.ad = 1; a.bd = 0; a.XL = dc->X; a.YL = dc->Y; }
-    const int hz = (g->kz - 1) / 2, pitch = 128 + 2 * hz;
+    a.LZ = x->Z >= 128 ? 128 : x->Z;
+    const int hz = (g->kz - 1) / 2, pitch = a.LZ + 2 * hz;
     // M = 128 always: the A rows beyond Cout read whatever follows the dc plane in shared memory; a row of A only
     // feeds its own row of D, and those TMEM lanes are never read
-    a.dc_plane = (uint32_t)((dc->C / 8) * 2048);
+    a.dc_plane = (uint32_t)((dc->C / 8) * a.LZ * 16);
     a.x_plane = (uint32_t)((x->C / 8) * pitch * 16);
     a.x_plane = (a.x_plane + 127) / 128 * 128;
     a.x_off = 2 * a.dc_plane;
@@ -239,7 +242,7 @@ int vsseg_conv3d_wgrad_tc(const vsseg_act8* x, const vsseg_act8* dc, const vsseg
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long nlines = (long)dc->B * a.XL * a.YL * (dc->Z / 128);
+    const long nlines = (long)dc->B * a.XL * a.YL * (dc->Z / a.LZ);
     long ns = sms / pairs;
     if (ns < 1) ns = 1;
     if (ns > nlines) ns = nlines;
