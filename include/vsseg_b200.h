@@ -255,6 +255,16 @@ int vsseg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
                     float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                     void* stream);
 
+/* Builds the weight image vsseg_conv3d_tc streams (layout above) from a torch-layout fp32 weight on the device:
+ * w is [d0][d1][kx][ky][kz]; conv_t_layout = 0: Conv3d [Cout][Cin] / 1: ConvTranspose3d [Cin][Cout]; phases = 1: the
+ * sub-pixel phase image of a stride-2 transposed conv (2 * n_split selections, x taps {1,-} and {2,0}, y unflipped);
+ * flip = 1: all three tap axes reversed (with conv_t_layout = 1 this is the adjoint of a stride-1 Conv3d, i.e. its
+ * data gradient, reference convolutions.py:125-156 under autograd).  Channels beyond the real ones are zero.
+ * out_bf16: 2 * n_sel * (cin_pad/16) * nj * kz * 2 * ky * (cout_pad/n_split) * 8 bf16 values. */
+int vsseg_pack_conv_weight_tc(const float* w, int32_t d0, int32_t d1, int32_t kx, int32_t ky, int32_t kz,
+                              int32_t conv_t_layout, int32_t phases, int32_t flip, int32_t cin_pad, int32_t cout_pad,
+                              int32_t n_split, void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -559,3 +559,42 @@ def test_fused_adam_matches_torch_adam():
     opt_a.zero_grad()
     (ps_a[0] * 2).sum().backward()
     assert opt_a.flat_grads()[0][:ps_a[0].numel()].eq(2).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cout,cin,k,mode,cin_pad,cout_pad,ns", [
+    (16, 16, (3, 3, 1), "conv", 16, 16, 1), (40, 80, (3, 3, 3), "conv", 80, 48, 3), (48, 32, (1, 1, 1), "conv", 32, 48, 1),
+    (32, 48, (3, 3, 1), "convT", 48, 32, 2), (64, 80, (3, 3, 3), "convT", 80, 64, 1),
+    (16, 32, (3, 3, 1), "adjoint", 16, 32, 1), (48, 96, (3, 3, 3), "adjoint", 48, 96, 2), (8, 24, (3, 3, 3), "adjoint", 16, 32, 1),
+])
+def test_native_weight_image_equals_python_packer(cout, cin, k, mode, cin_pad, cout_pad, ns):
+    """vsseg_pack_conv_weight_tc (one launch) must reproduce engine.pack_conv_weight_tc bit for bit: Conv3d image,
+    ConvTranspose3d sub-pixel phase image, and the adjoint (data-gradient) image of a stride-1 Conv3d."""
+    import torch.nn.functional as Fn
+    from vs_seg_b200 import lib as vlib
+    from vs_seg_b200.engine import pack_conv_weight_tc
+    dev = _dev()
+    lib = vlib.load()
+    g = torch.Generator().manual_seed(cout * 7 + cin)
+    s = torch.cuda.current_stream(dev).cuda_stream
+
+    def pad_to(w, d, c):
+        return w if w.shape[d] == c else Fn.pad(w, [0, 0] * (w.dim() - 1 - d) + [0, c - w.shape[d]])
+
+    if mode == "conv":
+        w = torch.randn((cout, cin) + k, generator=g).to(dev)
+        ref = pack_conv_weight_tc(pad_to(pad_to(w, 1, cin_pad), 0, cout_pad), False, ns)
+        flags = (0, 0, 0)
+    elif mode == "convT":
+        w = torch.randn((cin, cout) + k, generator=g).to(dev)          # ConvTranspose3d layout
+        ref = pack_conv_weight_tc(pad_to(pad_to(w, 0, cin_pad), 1, cout_pad), True, ns)
+        flags = (1, 1, 0)
+    else:   # w: stride-1 Conv3d weight [cout, cin, k]; the adjoint conv maps cout -> cin channels
+        w = torch.randn((cout, cin) + k, generator=g).to(dev)
+        wd = w.flip(2, 3, 4).transpose(0, 1).contiguous()             # [cin, cout, k] = Conv3d weight of the adjoint
+        ref = pack_conv_weight_tc(pad_to(pad_to(wd, 1, cin_pad), 0, cout_pad), False, ns)
+        flags = (1, 0, 1)
+    out = torch.empty(ref.numel(), dtype=torch.bfloat16, device=dev)
+    vlib.check(lib.vsseg_pack_conv_weight_tc(w.data_ptr(), w.shape[0], w.shape[1], *k, *flags, cin_pad, cout_pad, ns,
+                                             out.data_ptr(), s), "pack")
+    assert torch.equal(out.view(torch.int16), ref.reshape(-1).view(torch.int16))

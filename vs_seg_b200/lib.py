@@ -87,6 +87,7 @@ _SIGNATURES = {
     "vsseg_att_gate_bwd": (C.c_int, [_P(Act8), _P(F32View), _P(Act8), _P(Act8), _P(F32View), C.c_int32, C.c_void_p]),
     "vsseg_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int64, C.c_float, C.c_void_p]),
+    "vsseg_pack_conv_weight_tc": (C.c_int, [C.c_void_p] + [C.c_int32] * 11 + [C.c_void_p, C.c_void_p]),
     "vsseg_sw_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -17,6 +17,7 @@ attention-map gradients; parameters stay the module's own tensors, so torch.opti
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -48,6 +49,15 @@ class UNetTrainStep:
         self.B = x.shape[0]
         self.stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.tape = []
+        self._consts = {}
+        # PReLU slopes are kernel arguments: read ALL of them with one device->host copy per step (reading them
+        # block by block was a host sync in front of every Convolution block: the forward pass could never run ahead)
+        names = [n for n in dict(model.named_parameters()) if n.endswith("act.weight")]
+        if names:
+            vals = torch.cat([dict(model.named_parameters())[n].detach().reshape(-1)[:1] for n in names]).tolist()
+            self._slopes = dict(zip(names, vals))
+        else:
+            self._slopes = {}
         self.keep = []
         self.pgrads = {}          # parameter name -> fp32 grad tensor (torch layout)
         self.p = dict(model.named_parameters())
@@ -75,27 +85,60 @@ class UNetTrainStep:
         self.pgrads[name] = g if name not in self.pgrads else self.pgrads[name] + g
 
     def _ident_ep(self, bias, cpad):
-        scale = torch.ones(cpad, device=self.dev)
-        shift = torch.nn.functional.pad(bias.detach().float(), (0, cpad - bias.numel()))
-        self.keep += [scale, shift]
+        scale = self._const(cpad, 1.0)
+        shift = torch.nn.functional.pad(bias.detach().float(), (0, cpad - bias.numel())) if cpad != bias.numel() \
+            else bias.detach().float()
+        self.keep += [shift]
         return scale, shift
 
     # ---- convolution launches -------------------------------------------------------------------------
-    def _conv(self, src, dst, geom, w_conv_layout, transposed, scale, shift, slope=1.0, act=0, res=None):
-        """dst = act(conv(src)*scale + shift) [+ res]; w in torch layout (Conv3d, or ConvTranspose3d if transposed)."""
+    def _const(self, n, value):
+        """Cached all-ones / all-zeros epilogue vectors (one tiny launch per size instead of one per conv)."""
+        key = (n, value)
+        t = self._consts.get(key)
+        if t is None:
+            t = self._consts[key] = torch.full((n,), float(value), device=self.dev)
+        return t
+
+    def _pack_tc(self, w, transposed, adjoint, cin_pad, cout_pad, ns):
+        """Weight image of vsseg_conv3d_tc built by ONE native launch (vsseg_pack_conv_weight_tc) instead of ~12
+        torch launches.  w: the parameter in its own layout - Conv3d [Cout,Cin,k] (transposed=False), ConvTranspose3d
+        [Cin,Cout,k] (transposed=True: sub-pixel phase image); adjoint=True: w is a stride-1 Conv3d weight and the
+        image is that of its data-gradient conv (taps flipped, channel roles swapped)."""
+        w = w.detach()
+        if os.environ.get("VSSEG_NATIVE_PACK", "1") == "0":   # A/B switch: the torch-op packer this launch replaces
+            if adjoint:
+                w = w.flip(2, 3, 4).transpose(0, 1).contiguous()
+            return pack_conv_weight_tc(_pad_cout(_pad_cin(w, transposed, cin_pad), transposed, cout_pad), transposed, ns)
+        if not w.is_contiguous():
+            w = w.contiguous()
+        kx, ky, kz = w.shape[2:]
+        conv_t, phases, flip = (1, 0, 1) if adjoint else ((1, 1, 0) if transposed else (0, 0, 0))
+        nj = 2 if phases else kx
+        n = 2 * ns * (2 if phases else 1) * (cin_pad // 16) * nj * kz * 2 * ky * (cout_pad // ns) * 8
+        out = torch.empty(n, dtype=torch.bfloat16, device=self.dev)
+        self._chk(self.lib.vsseg_pack_conv_weight_tc(w.data_ptr(), w.shape[0], w.shape[1], kx, ky, kz, conv_t, phases, flip,
+                                                     cin_pad, cout_pad, ns, out.data_ptr(), self.stream), "pack_conv_weight_tc")
+        return out
+
+    def _conv(self, src, dst, geom, w_conv_layout, transposed, scale, shift, slope=1.0, act=0, res=None, adjoint=False):
+        """dst = act(conv(src)*scale + shift) [+ res]; w in torch layout (Conv3d, or ConvTranspose3d if transposed;
+        adjoint: the stride-1 Conv3d weight whose data-gradient conv this is)."""
         cpad = _round_up(dst.C, 16)
         ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, act)
         res_p = C.byref(res) if res is not None else None
         ns = 0
         if src.C % 16 == 0:
             ns = self.lib.vsseg_conv3d_tc_suggest_split(C.byref(src), C.byref(dst), C.byref(geom), None)
-        w_conv_layout = _pad_cin(w_conv_layout, transposed, src.C)   # zero weights for zero-padded input channels
         if ns > 0:
-            w = pack_conv_weight_tc(_pad_cout(w_conv_layout, transposed, dst.C), transposed, ns)
+            w = self._pack_tc(w_conv_layout, transposed, adjoint, src.C, cpad, ns)
             self.keep.append(w)
             self._chk(self.lib.vsseg_conv3d_tc(C.byref(src), C.byref(dst), C.byref(geom), w.data_ptr(), ns, C.byref(ep),
                                                res_p, None, None, None, None, None, None, self.stream), "conv3d_tc")
         else:
+            if adjoint:
+                w_conv_layout = w_conv_layout.detach().flip(2, 3, 4).transpose(0, 1).contiguous()
+            w_conv_layout = _pad_cin(w_conv_layout, transposed, src.C)   # zero weights for zero-padded input channels
             w = pack_conv_weight(w_conv_layout, transposed, cpad)
             self.keep.append(w)
             self._chk(self.lib.vsseg_conv3d_act8(C.byref(src), C.byref(dst), C.byref(geom), w.data_ptr(), cpad, C.byref(ep),
@@ -105,13 +148,11 @@ class UNetTrainStep:
         """Data gradient of a (transposed) conv = its adjoint convolution with the same weights."""
         dx = gx.buf.view(c0, Cx)
         cpad = _round_up(dx.C, 16)
-        scale = torch.ones(cpad, device=self.dev)
-        shift = torch.zeros(cpad, device=self.dev)
-        self.keep += [scale, shift]
+        scale, shift = self._const(cpad, 1.0), self._const(cpad, 0.0)
         acc = gx.filled
         if not transposed and tuple(stride) == (1, 1, 1):
-            wd = w.detach().flip(2, 3, 4).transpose(0, 1).contiguous()      # Conv3d weight [Cin, Cout, k] of the adjoint
-            self._conv(dc, dx, self._geom(k), wd, False, scale, shift, res=dx if acc else None)
+            # adjoint of a stride-1 Conv3d: Conv3d with the taps flipped and the channel roles swapped
+            self._conv(dc, dx, self._geom(k), w, False, scale, shift, res=dx if acc else None, adjoint=True)
         elif not transposed:
             # strided Conv3d: adjoint = ConvTranspose3d whose weight tensor [in=Cout, out=Cin, k] is W itself
             self._conv(dc, dx, self._geom(k, stride, True), w.detach(), True, scale, shift, res=dx if acc else None)
@@ -153,7 +194,7 @@ class UNetTrainStep:
         w, bias = self.p[prefix + "conv.weight"], self.p[prefix + "conv.bias"]
         gamma, beta = self.p[prefix + "norm.weight"], self.p[prefix + "norm.bias"]
         slope_t = self.p[prefix + "act.weight"]
-        slope = float(slope_t.detach().reshape(-1)[0])
+        slope = self._slopes[prefix + "act.weight"]
         Cc = dst.C
         cbuf = Act8Buffer(dst.B, Cc, dst.X, dst.Y, dst.Z, self.dev)
         self.keep.append(cbuf)
