@@ -1033,6 +1033,9 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     P->estr[3] = 1; P->estr[4] = 1;
     P->smem = TC_HDR + (size_t)a.nstage * a.stage_bytes;
     P->grid = (unsigned)(a.ntiles < sms ? a.ntiles : sms);   // persistent: one CTA per SM
+    // transposed conv: the x phase is the fastest tile index and the odd phase stages twice the planes of the even
+    // one; with an even grid every CTA would keep one phase for all its tiles (2x imbalance) - an odd grid alternates
+    if (a.npx == 2 && a.ntiles > (int)P->grid && P->grid % 2 == 0) P->grid -= 1;
     return true;
 }
 
