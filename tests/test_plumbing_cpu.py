@@ -88,3 +88,25 @@ def test_vsparams_train_and_inference_recipe_on_cpu(tmp_path, monkeypatch):
     assert seg.shape == (48, 56, 12) and set(np.unique(seg)) <= {0, 1}
     for h in list(p.logger.handlers):
         p.logger.removeHandler(h)
+
+
+def test_fused_adam_on_cpu_is_torch_adam():
+    """CPU parameters (the reference's --debug plumbing run) go through torch.optim.Adam unchanged, including the
+    learning-rate halving the training loop does through optimizer.param_groups (reference VSparams.py:517-523)."""
+    import torch
+    from vs_seg_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    a = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oa, ob = FusedAdam(a, lr=1e-2, weight_decay=1e-3), torch.optim.Adam(b, lr=1e-2, weight_decay=1e-3)
+    for it in range(5):
+        for o, ps in ((oa, a), (ob, b)):
+            o.zero_grad()
+            sum((p * (i + 1 + it)).sum() for i, p in enumerate(ps)).backward()
+            if it == 2:
+                for g in o.param_groups:
+                    g["lr"] = g["lr"] / 2
+            o.step()
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
+    assert oa.flat_grads() == []
