@@ -4,6 +4,8 @@
 // stride-1 convolutions lives in vsseg_tc.cu.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "vsseg_common.cuh"
 
 namespace vsseg {
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(128) conv_cin1_kernel(const Cin1Args a) {
 // y outputs at one (x, z): 18 coalesced input loads (3 x planes x 6 y lines) feed 4 x 16 accumulators, every
 // 128-bit shared-memory weight read is used for 16 FMAs.  ~290 instructions per voxel (the generic kernel
 // above: ~1100, instruction-bound at 90 us for a 128^3 patch).
-constexpr int CIN1_YB = 4;
+template <int CIN1_YB>
 __global__ void __launch_bounds__(128) conv_cin1_k331_kernel(const Cin1Args a) {
     __shared__ float4 ws4[9 * 4];      // [tap][16]
     __shared__ float4 ep4[2 * 4];      // scale[16], shift[16]
@@ -631,8 +633,11 @@ int vsseg_conv3d_cin1(const vsseg_f32view* in, const vsseg_act8* out, const vsse
     const int64_t nvox = (int64_t)out->B * out->X * out->Y * out->Z;
     const unsigned nblk = (unsigned)((int64_t)out->B * out->X * out->Y * ((out->Z + 127) / 128));
     if (g->kx == 3 && g->ky == 3 && g->kz == 1 && ep->act != 1) {
-        const unsigned nb4 = (unsigned)((int64_t)out->B * out->X * ((out->Y + CIN1_YB - 1) / CIN1_YB) * ((out->Z + 127) / 128));
-        conv_cin1_k331_kernel<<<nb4, 128, 0, (cudaStream_t)stream>>>(a);
+        static const int yb = getenv("VSSEG_CIN1_YB") ? atoi(getenv("VSSEG_CIN1_YB")) : 4;   // y outputs per thread (tuning knob)
+        const int YB = yb == 2 ? 2 : 4;
+        const unsigned nb4 = (unsigned)((int64_t)out->B * out->X * ((out->Y + YB - 1) / YB) * ((out->Z + 127) / 128));
+        if (YB == 2) conv_cin1_k331_kernel<2><<<nb4, 128, 0, (cudaStream_t)stream>>>(a);
+        else conv_cin1_k331_kernel<4><<<nb4, 128, 0, (cudaStream_t)stream>>>(a);
     } else {
         conv_cin1_kernel<16><<<nblk, 128, 0, (cudaStream_t)stream>>>(a);
     }
