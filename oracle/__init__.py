@@ -16,6 +16,9 @@ modules imported in the build container under ``oracle/monai_shim`` (see
 ``oracle/make_golden.py`` and ``tests/golden/``).  ``sliding_window_inference``
 lives in MONAI 0.4.0, which is absent from /root/reference and not installable
 offline: that function is restated from the published MONAI 0.4.0 algorithm and
-is "parity unpinned" against MONAI itself (it is pinned only against hand-worked
-window lists in ``tests/test_oracle_sliding_window.py``).
+is "parity unpinned" against MONAI itself.  It is frozen by
+``tests/golden/sw_geometry.json`` (``oracle/make_sw_golden.py``) and checked in
+``tests/test_oracle_sliding_window.py`` against window lists worked by hand, the closed-form
+erf weights and the SURVEY.md §8a S1 probe numbers (window counts, w[0]/w[64], multiplicity
+histogram of the 384x384x160 / 128^3 benchmark geometry).
 """
