@@ -104,25 +104,15 @@ def build_net(device):
     return net.to(device).eval(), sd
 
 
-def cpu_oracle_patches(sd, vol, max_patches, budget_s):
-    """Times the CPU oracle (torch fp32, all host threads) on the first windows of `vol`."""
-    from oracle import sw_oracle, unet_oracle
-    torch.set_num_threads(os.cpu_count() or 1)
-    starts = sw_oracle.window_starts(VOLUME, ROI, sw_oracle.scan_interval(VOLUME, ROI, 0.25))
-    outs, t_total, n = [], 0.0, 0
-    with torch.no_grad():
-        for j, s in enumerate(starts[: max_patches + 1]):
-            w = vol[:, :, s[0]:s[0] + ROI[0], s[1]:s[1] + ROI[1], s[2]:s[2] + ROI[2]]
-            t0 = time.perf_counter()
-            y = unet_oracle.unet_forward(sd, w)[0]
-            dt = time.perf_counter() - t0
-            outs.append((s, y))
-            if j > 0:  # first patch is the warm-up
-                t_total += dt
-                n += 1
-            if t_total > budget_s:
-                break
-    return outs, n, t_total
+def bench_config(world):
+    """The workload description both arms print (the driver compares the two dicts)."""
+    group = int(os.environ.get("VSSEG_SW_GROUP", "8"))
+    return {"workload": "VS_inference sliding-window 384x384x160, 128^3 window (configs[3])",
+            "volume": list(VOLUME), "roi": list(ROI), "overlap": 0.25, "blend": "gaussian",
+            "patches_per_step": 32, "weights": "seeded random init",
+            "l2_policy": f"GPU arm: {N_ROT} rotating volumes (283 MB each) > 126 MB L2",
+            "gpu_schedule": f"window groups of {group}, one captured CUDA graph per volume; "
+                            + (f"patch-index shard x{world}, 1 NCCL reduce/volume" if world > 1 else "1 GPU")}
 
 
 def run_reference(args):
@@ -151,8 +141,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "VS_inference sliding-window 384x384x160, 128^3 window (configs[3])",
-                   "volume": list(VOLUME), "roi": list(ROI), "overlap": 0.25, "blend": "gaussian"},
+        "config": bench_config(args.gpus),
         "cpu_baseline": {"value": val, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -167,7 +156,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -277,6 +265,15 @@ def main():
         ms_e2e, _ = timed(step_e2e, 2, args.steps)
         clk = clocks.stop() if rank == 0 else None
 
+        # parity leg, part 1 (all ranks): the SAME call the timed region makes, on synthetic volume 0 - window
+        # groups of 8 through the captured graph, blend in the last kernel, (N > 1: NCCL reduce), finalise
+        par_res = None
+        if not args.no_cpu_baseline:
+            res = infer(vols[0][0], vols[0][1])
+            if res is not None:
+                par_res = (res[0].cpu(), res[1].cpu(), res[2].cpu())
+            torch.cuda.synchronize(dev)
+
         if rank != 0:
             dist.destroy_process_group()
             return
@@ -313,40 +310,75 @@ def main():
             roof = {"bound": "hbm", "achieved": top[3] / (top[4] * 1e-3) / 1e9, "peak": pk_h / 1e9, "unit": "GB/s"}
         traffic = None
         try:   # dram bytes of the same launch from the committed ncu --set full capture (profiles/)
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_group_summary.json")))
+            import glob
+            ncu = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_group_summary.json")))[-1]))
             hit = [e for e in ncu["launches"] if e["step"] == top[0]]
             if hit and hit[0].get("dram_rd_MB") is not None:
                 traffic = (hit[0]["dram_rd_MB"] + hit[0]["dram_wr_MB"]) * 1e6
         except (OSError, KeyError, ValueError):
             pass
         tc_ms = sum(p[4] for p in prof if p[1] == "tcgen05")
+        # per-launch roofline time: max(3 x FLOP / tensor peak, algorithmic bytes / HBM peak)  (bf16x3 issues three
+        # MMAs per product; bytes follow SURVEY.md §8d: every activation read once per consumer and written once, 4 B)
         roof_ms = sum(max(3 * p[2] / pk_t, p[3] / pk_h) for p in prof) * 1e3
+        timed_patch_ms = ms / args.steps / (n_win / world)
         roof.update({"frac": roof["achieved"] / roof["peak"], "traffic": traffic, "kernel": "conv_tc_kernel" if top[1] == "tcgen05" else top[0],
                      "launch": top[0], "alg_bytes_per_launch": top[3], "alg_flops_per_launch": top[2],
                      "kernel_ms": top[4], "share_of_group": top[4] / group_ms,
                      "conv_tc_kernel_share_of_group": tc_ms / group_ms,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
-                     "whole_group_frac_of_roofline": roof_ms / group_ms,
-                     "useful_tflops_whole_patch": plan.total_flops() / (group_ms * 1e-3) / 1e12})
+                     "per_launch_frac_definition": "max(3*FLOP/tensor_peak, alg_bytes/hbm_peak) / kernel_ms",
+                     "whole_patch": {
+                         "alg_gflop": plan.total_flops() / group / 1e9,
+                         "alg_gbytes": sum(p[3] for p in prof) / group / 1e9,
+                         "roofline_ms": roof_ms / group,
+                         "survey_roofline_ms_bf16x3_4B": 0.755,
+                         "profiled_ms": patch_ms, "timed_ms": timed_patch_ms,
+                         "frac_profiled": roof_ms / group_ms, "frac_timed": roof_ms / group / timed_patch_ms,
+                         "frac_timed_vs_survey": 0.755 / timed_patch_ms,
+                         "useful_tflops": plan.total_flops() / (group_ms * 1e-3) / 1e12},
+                     "launches": [{"launch": p[0], "ms": round(p[4], 4), "gflop": round(p[2] / 1e9, 3),
+                                   "mbytes": round(p[3] / 1e6, 1),
+                                   "frac": round(max(3 * p[2] / pk_t, p[3] / pk_h) * 1e3 / p[4], 3)}
+                                  for p in sorted(prof, key=lambda q: -q[4])[:12]]})
 
-        # ---- CPU baseline (the oracle on the host cores) + parity of the native logits against it
+        # ---- CPU baseline (the oracle on the host cores) + parity of the timed configuration against it:
+        # the whole finalised 384x384x160 volume of the call above vs sw_oracle driving the oracle network over
+        # all 32 windows (sw_batch_size 1, as VSparams.py:568-574); the oracle's per-window time is the CPU baseline
         cpu = None
         parity = None
-        if not args.no_cpu_baseline:
-            outs, n, t = cpu_oracle_patches(sd, host[0][0], max_patches=8, budget_s=args.cpu_budget_s)
-            cpu = {"value": n / t, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"{n} consecutive 128^3 windows of synthetic volume 0 after 1 warm-up window, "
-                             f"torch {torch.__version__} fp32, {os.cpu_count()} host cpus"}
-            err, flips, ties = 0.0, 0, 0
-            plan1 = net.eval_plan(ROI, batch=1, device=dev)
-            for s, y in outs:
-                got = plan1.forward(vol0[:, :, s[0]:s[0] + ROI[0], s[1]:s[1] + ROI[1], s[2]:s[2] + ROI[2]].contiguous())[0].cpu()
-                err = max(err, (got - y).abs().max().item())
-                margin = (y[:, 1] - y[:, 0]).abs()
-                flips += ((got.argmax(1) != y.argmax(1)) & (margin > 1e-4)).sum().item()
-                ties += (margin <= 1e-4).sum().item()
-            parity = {"max_abs_err_logits": err, "argmax_flips_margin_gt_1e-4": flips, "near_ties_le_1e-4": ties,
-                      "windows_checked": len(outs), "tolerance": 1e-3}
+        if not args.no_cpu_baseline and par_res is not None:
+            from oracle import loss_oracle, sw_oracle, unet_oracle
+            torch.set_num_threads(os.cpu_count() or 1)
+            times = []
+
+            def oracle_predictor(w):
+                t0 = time.perf_counter()
+                y = unet_oracle.unet_forward(sd, w)[0]
+                times.append(time.perf_counter() - t0)
+                return y
+
+            with torch.no_grad():
+                ref = sw_oracle.sliding_window_inference(host[0][0], ROI, 1, oracle_predictor, mode="gaussian")
+            timed_t = times[1:] if len(times) > 1 else times   # the first window is the warm-up
+            cpu = {"value": len(timed_t) / sum(timed_t), "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{len(timed_t)} consecutive 128^3 windows of synthetic volume 0 after 1 warm-up window "
+                             f"({sum(timed_t):.1f} s), torch {torch.__version__} fp32, {os.cpu_count()} host cpus"}
+            got, mask, sums = par_res
+            label = host[0][1]
+            margin = (ref[:, 1] - ref[:, 0]).abs()
+            ref_mask = ref.argmax(1, keepdim=True)
+            diff_mask = mask.long() != ref_mask
+            dice_native = ((2 * sums[0, 0] + 1e-5) / (sums[0, 1] + sums[0, 2] + 1e-5)).item()
+            parity = {"scope": "full finalised volume of the timed call (window groups of 8, captured graph, blend in the "
+                               "last kernel" + (f", NCCL reduce over {world} ranks" if world > 1 else "") + ") vs sw_oracle",
+                      "max_abs_err_logits": (got - ref).abs().max().item(),
+                      "argmax_flips_margin_gt_1e-4": ((got.argmax(1) != ref.argmax(1)) & (margin > 1e-4)).sum().item(),
+                      "mask_kernel_flips_margin_gt_1e-4": (diff_mask[:, 0] & (margin > 1e-4)).sum().item(),
+                      "near_ties_le_1e-4": (margin <= 1e-4).sum().item(),
+                      "dice_mask_native": dice_native,
+                      "dice_mask_oracle": loss_oracle.dice_score(ref, label).item(),
+                      "windows_checked": len(times), "voxels_checked": ref[:, 0].numel(), "tolerance": 1e-3}
 
         in_bytes = h2d_bytes
         out_bytes = mask_host.numel() + sums_host.numel() * 8
@@ -355,12 +387,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16x3->f32",
             "data": "synthetic",
-            "config": {"workload": "VS_inference sliding-window 384x384x160, 128^3 window (configs[3])",
-                       "volume": list(VOLUME), "roi": list(ROI), "overlap": 0.25, "blend": "gaussian",
-                       "patches_per_step": n_win, "window_group": group, "windows_per_rank": n_win // world,
-                       "weights": "seeded random init",
-                       "l2_policy": f"{N_ROT} rotating volumes (283 MB each) > 126 MB L2",
-                       "parallelism": f"patch-index shard x{world}, 1 NCCL reduce/volume" if world > 1 else "1 GPU"},
+            "config": bench_config(world),
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "parity": parity,

@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define VSSEG_EINVAL 100001
-#define VSSEG_ABI_VERSION 1
+#define VSSEG_ABI_VERSION 2
 
 /*
  * act8: channel-blocked split-bf16 activation tensor.
@@ -44,11 +44,20 @@ typedef struct {
 } vsseg_act8;
 
 /* fp32 tensor addressed by strides (elements): used for the 1-channel network input, read in
- * place from the full volume (the sliding-window gather is free), and for planar outputs. */
+ * place from the full volume (the sliding-window gather is free), and for planar outputs.
+ * `indirect` (optional) makes the view relocatable: it is the DEVICE address of an 8-byte cell that holds
+ * the base address of the volume, and `ptr` is then the BYTE OFFSET of the region from that base.  The
+ * kernel reads the cell at run time, so a captured CUDA graph of a whole sliding-window schedule
+ * (MONAI sliding_window_inference, reference call site VSparams.py:568-574) is re-targeted to another
+ * volume by one 8-byte store.  Honoured by the forward kernels (vsseg_conv3d_cin1, vsseg_conv3d_tc*,
+ * vsseg_conv3d_act8, vsseg_conv3d_smallcout, vsseg_conv3d_gate_logits, vsseg_att_gate); the layout
+ * conversion and training entry points reject it. */
 typedef struct {
-    float*  ptr;           /* element (b=0, c=0, x=0, y=0, z=0) of the region */
+    float*  ptr;           /* element (b=0, c=0, x=0, y=0, z=0) of the region (byte offset if indirect) */
     int64_t sb, sc, sx, sy, sz;
     int32_t B, C, X, Y, Z;
+    int32_t reserved;      /* 0 */
+    const int64_t* indirect; /* NULL, or device cell holding the base address */
 } vsseg_f32view;
 
 /* Per-output-channel epilogue y = act(acc * scale[c] + shift[c]):
@@ -97,8 +106,8 @@ int vsseg_conv3d_act8(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
  * accumulators), TMA-staged input boxes, same epilogue/residual contract as vsseg_conv3d_act8.
  * Covers Conv3d (stride 1 or 2 per axis, kernel 1 or 3 per axis) and ConvTranspose3d (stride (2,2,1|2),
  * kernel (3,3,1|3), output_padding = stride-1; reference convolutions.py:114-135) with Cin % 16 == 0,
- * Cout % 8 == 0 and a z extent of the M grid (output grid; input grid when transposed) that is a
- * multiple of 128 or one of 8..64 dividing 128.  vsseg_conv3d_tc_supported returns 1 when the shape is
+ * Cout % 8 == 0; the M tile (128 positions of the output grid; input grid when transposed) is LY y lines x LZ z
+ * with LZ the largest power of two (<= 128) dividing the z extent.  vsseg_conv3d_tc_supported returns 1 when the shape is
  * covered; vsseg_conv3d_tc_suggest_split returns the n_split (CTAs per M tile along Cout) that fills
  * the chip for small layers, or 0 when the shape is not covered.
  *
@@ -166,16 +175,31 @@ int vsseg_conv3d_smallcout(const vsseg_act8* in, const vsseg_f32view* out, const
                            const float* w, const float* bias, int32_t act, float slope,
                            const float* sw_weight, void* stream);
 
+/* Top of the decoder in one bandwidth-bound launch: AttentionBlock2 gate x*(1+att) (reference
+ * attentionblock.py:44-47) applied on the fly to the input of the last ResidualUnit (conv_only unit + 1x1x1
+ * shortcut folded into the centre tap, unet2d5_spvPA.py:186-190; kernel (3,3,1), Cout 1 or 2), so the gated
+ * 2c-channel tensor is never written: out = conv(x * (1 + att)) + bias, stored or, with sw_weight, blended
+ * into the sliding-window accumulator (out += sw_weight * y, MONAI step 6, VSparams.py:568-574).
+ *   x: act8 [B,Cin,X,Y,Z], Cin % 8 == 0, Cin <= 32;  att: [B,1,X,Y,Z] or NULL (no gate)
+ *   w_host: HOST fp32 [9 taps (tx*3+ty)][Cin][Cout]; bias_host: HOST [Cout] (passed to the kernel by value)
+ *   outs: n_outs views [*,Cout,X,Y,Z]; n_outs == 1: one view covering all B entries, n_outs == B: entry b -> outs[b]
+ *   (the windows of a sliding-window group land at different offsets of the accumulator). */
+int vsseg_conv3d_gate_logits(const vsseg_act8* x, const vsseg_f32view* att, const float* w_host,
+                             const float* bias_host, int32_t cout, const vsseg_f32view* outs, int32_t n_outs,
+                             const float* sw_weight, void* stream);
+
 /* Attention gate, AttentionBlock2: out = x * (1 + att) (reference attentionblock.py:44-47).
  * att: planar fp32 [B,1,X,Y,Z]; x/out act8 with the same shape (may alias). */
 int vsseg_att_gate(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_act8* out, void* stream);
 
-/* Sliding-window finalise: prob = acc / cnt (MONAI step 7), optional argmax mask (uint8) and
- * hard-Dice partial sums vs label (VSparams.compute_dice_score, VSparams.py:393-408):
- * sums[0] += |pred&label|, sums[1] += |label|, sums[2] += |pred| (fp64 accumulators).
- * acc/out: [C,n] planar; cnt: [n]; label: [n] float 0/1 or NULL; mask: [n] or NULL. */
+/* Sliding-window finalise: prob = acc / cnt (MONAI step 7; cnt == NULL: prob = acc, no division), optional
+ * argmax mask (uint8) and hard-Dice partial sums vs label (VSparams.compute_dice_score, VSparams.py:393-408:
+ * argmax -> one_hot -> 1 - DiceLoss(include_background=False)):
+ * sums[0] += |pred&label|, sums[1] += |label|, sums[2] += |pred| (fp64 accumulators), pred = (argmax == 1).
+ * acc/out: [C,n] planar (out may be NULL); cnt: [n]; label: [n] float 0/1 (label_u8 = 0) or uint8 (label_u8 = 1),
+ * or NULL; mask: [n] or NULL.  128-bit accesses when n % 4 == 0 and the pointers are 16-byte aligned. */
 int vsseg_sw_finalize(const float* acc, const float* cnt, float* out, int32_t C, int64_t n,
-                      uint8_t* mask, const float* label, double* sums, void* stream);
+                      uint8_t* mask, const void* label, int32_t label_u8, double* sums, void* stream);
 
 /* ---- Dice_spvPA loss (reference params/losses/dice_spvPA.py:90-167, :238-297) -----------------------
  * All tensors planar fp32, contiguous.  The loss is assembled from "terms": the 2-class logits term
@@ -199,6 +223,21 @@ int vsseg_dice_finalize(const double* sums, const float* row_scale, int32_t nrow
 int vsseg_dice_backward(const float* pred, const float* target, int32_t B, int32_t C, int64_t n,
                         float hardness_lambda, const float* coef, const float* grad_out, float* grad,
                         void* stream);
+
+/* General DiceLoss.forward (reference dice_spvPA.py:90-167) for up to 8 channels, every constructor flag:
+ *   act 0 none | 1 sigmoid | 2 softmax over the channels (:105-113); target_is_labels: target is [B,1,n] integer labels
+ *   turned into a one-hot (:114-118), else dense [B,C,n]; weight: optional hardness weight [B,C,n] (:136-149);
+ *   squared: squared_pred (:141-143).
+ *   vsseg_dice_general_sums      sums[b][c][0..2] += (sum w t p, sum w t', sum w p')  (fp64, stride 8 channels per batch
+ *                                entry: sums is [B][8][3], zeroed by the caller); include_background / jaccard / reduction
+ *                                act on these B x C numbers and stay with the caller
+ *   vsseg_dice_general_backward  grad[b][c][v] = d/d pred of sum_c (gI_c I_c + gP_c P_c) through the activation;
+ *                                grad_sums float [B][8][3] = (gI, gG, gP); the weight is treated as a constant */
+int vsseg_dice_general_sums(const float* pred, const float* target, const float* weight, int32_t B, int32_t C, int64_t n,
+                            int32_t act, int32_t target_is_labels, int32_t squared, double* sums, void* stream);
+int vsseg_dice_general_backward(const float* pred, const float* target, const float* weight, int32_t B, int32_t C,
+                                int64_t n, int32_t act, int32_t target_is_labels, int32_t squared,
+                                const float* grad_sums, float* grad, void* stream);
 
 /* ---- training mode (reference convolutions.py:148-156 Conv -> BatchNorm3d -> Dropout -> PReLU, autograd) -----
  * Convolutions (forward and data gradient) use vsseg_conv3d_tc: the data gradient of a Conv3d is the

@@ -47,6 +47,62 @@ def _save_png(path, panels):
     return True
 
 
+def _plot_png(path, panels, size=(600, 400)):
+    """Line plots side by side with PIL (the image has no matplotlib): panels = [(title, xs, ys, xlabel)]."""
+    try:
+        from PIL import Image, ImageDraw
+    except ImportError:
+        return False
+    W, H = size
+    img = Image.new("RGB", (W * len(panels), H), "white")
+    d = ImageDraw.Draw(img)
+    for k, (title, xs, ys, xlabel) in enumerate(panels):
+        x0, y0, x1, y1 = k * W + 60, 40, (k + 1) * W - 20, H - 50
+        d.rectangle([x0, y0, x1, y1], outline="black")
+        d.text((x0 + 5, 12), title, fill="black")
+        d.text(((x0 + x1) // 2 - 15, H - 25), xlabel, fill="black")
+        if len(xs):
+            lo, hi = float(min(ys)), float(max(ys))
+            hi = hi if hi > lo else lo + 1.0
+            xl, xh = float(min(xs)), float(max(xs))
+            xh = xh if xh > xl else xl + 1.0
+            pts = [(x0 + (x - xl) / (xh - xl) * (x1 - x0), y1 - (y - lo) / (hi - lo) * (y1 - y0)) for x, y in zip(xs, ys)]
+            if len(pts) > 1:
+                d.line(pts, fill=(31, 119, 180), width=2)
+            for px, py in pts:
+                d.ellipse([px - 2, py - 2, px + 2, py + 2], fill=(31, 119, 180))
+            d.text((k * W + 5, y0 - 5), f"{hi:.4g}", fill="black")
+            d.text((k * W + 5, y1 - 5), f"{lo:.4g}", fill="black")
+            d.text((x0, y1 + 5), f"{xl:g}", fill="black")
+            d.text((x1 - 25, y1 + 5), f"{xh:g}", fill="black")
+    img.save(path)
+    return True
+
+
+def _hist_png(path, values, bins, size=(600, 400)):
+    """Histogram bar chart with PIL (reference: plt.hist(dice_scores, bins=np.arange(0, 1.01, 0.01)))."""
+    try:
+        from PIL import Image, ImageDraw
+    except ImportError:
+        return False
+    counts, edges = np.histogram(np.asarray(values, dtype=np.float64), bins=bins)
+    W, H = size
+    img = Image.new("RGB", (W, H), "white")
+    d = ImageDraw.Draw(img)
+    x0, y0, x1, y1 = 50, 30, W - 20, H - 40
+    d.rectangle([x0, y0, x1, y1], outline="black")
+    top = max(int(counts.max()), 1)
+    bw = (x1 - x0) / len(counts)
+    for i, c in enumerate(counts):
+        if c:
+            d.rectangle([x0 + i * bw, y1 - c / top * (y1 - y0), x0 + (i + 1) * bw, y1], fill=(31, 119, 180))
+    d.text((5, y0 - 5), str(top), fill="black")
+    d.text((x0, y1 + 5), f"{edges[0]:g}", fill="black")
+    d.text((x1 - 20, y1 + 5), f"{edges[-1]:g}", fill="black")
+    img.save(path)
+    return True
+
+
 class VSparams:
     def __init__(self, parser):
         parser.add_argument("--debug", dest="debug", action="store_true", help="activate debugging mode")
@@ -87,7 +143,12 @@ class VSparams:
         if self.debug:
             self.pad_crop_shape_test = [128, 128, 32]
         self.num_workers = 4
-        self.torch_device_arg = args.device or ("cuda:0" if torch.cuda.is_available() else "cpu")
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        # the reference hard-codes cuda:0 (VSparams.py:83); under torchrun every rank drives its own GPU
+        default_gpu = f"cuda:{self.local_rank}" if self.world_size > 1 else "cuda:0"
+        self.torch_device_arg = args.device or (default_gpu if torch.cuda.is_available() else "cpu")
         self.train_batch_size = args.train_batch_size
         self.initial_learning_rate = args.initial_learning_rate
         self.epochs_with_const_lr = 100
@@ -120,8 +181,13 @@ class VSparams:
         self.figures_path = os.path.join(self.results_folder_path, "figures")
 
         self.device = torch.device(self.torch_device_arg)
-        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
-        self.rank = int(os.environ.get("RANK", "0"))
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        if self.world_size > 1:
+            # one process group for the whole run, created before any rank touches the data set
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group("nccl" if self.device.type == "cuda" else "gloo")
 
     def create_results_folders(self):
         for path in (self.logs_path, self.model_path, self.figures_path):
@@ -132,6 +198,9 @@ class VSparams:
     def set_up_logger(self, log_file_name):
         os.makedirs(self.logs_path, exist_ok=True)
         self.logger = logging.getLogger()
+        if self.rank != 0:   # replicas log next to rank 0's file instead of truncating it
+            stem, ext = os.path.splitext(log_file_name)
+            log_file_name = f"{stem}_rank{self.rank}{ext}"
         file_handler = logging.FileHandler(os.path.join(self.logs_path, log_file_name), mode="w")
         console_handler = logging.StreamHandler()
         self.logger.addHandler(file_handler)
@@ -167,6 +236,9 @@ class VSparams:
             if missing:
                 logger.info("Writing synthetic cases for the split (no dataset present)...")
                 dataio.make_synthetic_dataset(self.data_root, self.split_csv, self.dataset, self.synthetic_shape)
+        if self.synthetic and self.world_size > 1:
+            import torch.distributed as dist
+            dist.barrier()   # the other ranks wait for rank 0's files
         with open(self.split_csv) as csvfile:
             for row in csv.reader(csvfile):
                 if not row:
@@ -302,7 +374,11 @@ class VSparams:
         return FusedAdam(model.parameters(), lr=self.initial_learning_rate, weight_decay=self.weight_decay)
 
     def compute_dice_score(self, predicted_probabilities, label):
-        """Hard foreground Dice of the argmax segmentation (reference VSparams.py:393-408)."""
+        """Hard foreground Dice of the argmax segmentation (reference VSparams.py:393-408).  CUDA tensors: one
+        native launch (argmax + Dice sums, vsseg_sw_finalize), result stays on the device - no host sync."""
+        if predicted_probabilities.is_cuda:
+            from vs_seg_b200.sliding_window import hard_dice
+            return hard_dice(predicted_probabilities, label).mean().float().reshape(1, 1)
         from vs_seg_b200.compat import one_hot
         n_classes = predicted_probabilities.shape[1]
         y_pred = torch.argmax(predicted_probabilities, dim=1, keepdim=True)
@@ -313,11 +389,13 @@ class VSparams:
     def run_training_algorithm(self, model, loss_function, optimizer, train_loader, val_loader):
         logger = self.logger
         logger.info("Running the training loop...")
-        try:
-            from torch.utils.tensorboard import SummaryWriter
-            tb_writer = SummaryWriter()
-        except Exception:  # tensorboard is optional plumbing
-            tb_writer = None
+        tb_writer = None
+        if self.rank == 0:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                tb_writer = SummaryWriter()
+            except Exception:  # tensorboard is optional plumbing
+                tb_writer = None
 
         epochs_with_const_lr = self.epochs_with_const_lr
         val_interval = self.val_interval
@@ -328,9 +406,6 @@ class VSparams:
         # gradient per step (vs_seg_b200.ddp); a single process is the reference's own loop
         from vs_seg_b200 import ddp
         if self.world_size > 1:
-            import torch.distributed as dist
-            if not dist.is_initialized():
-                dist.init_process_group("nccl" if str(self.device).startswith("cuda") else "gloo")
             ddp.broadcast_module_state(model)
         reducer = ddp.GradReducer(model, optimizer)
         start = perf_counter()
@@ -373,11 +448,13 @@ class VSparams:
                         dice_score = self.compute_dice_score(val_outputs[0], val_labels)
                         loss = loss_function(val_outputs, val_labels)
                         # the reference accumulates these twice per image (VSparams.py:490-496), which doubles the
-                        # logged validation loss and leaves the metric ratio unchanged; kept for log compatibility
+                        # logged validation loss and leaves the metric ratio unchanged; kept for log compatibility.
+                        # The sums stay on the device: one host read per validation pass instead of three per image
                         for _ in range(2):
                             metric_count += len(dice_score)
-                            metric_sum += dice_score.sum().item()
-                            epoch_loss_val += loss.item()
+                            metric_sum = metric_sum + dice_score.sum()
+                            epoch_loss_val = epoch_loss_val + loss.detach()
+                    metric_sum, epoch_loss_val = float(metric_sum), float(epoch_loss_val)
                     metric = metric_sum / metric_count
                     metric_values.append(metric)
                     epoch_loss_val /= step
@@ -405,7 +482,9 @@ class VSparams:
         return epoch_loss_values, metric_values
 
     def plot_loss_curve_and_mean_dice(self, epoch_loss_values, metric_values):
-        """Curves as CSV (always) — the reference's matplotlib figure needs a package this image lacks."""
+        """The reference's two-panel figure (VSparams.py:530-545), drawn with PIL, plus the same curves as CSV."""
+        if self.rank != 0:
+            return
         os.makedirs(self.figures_path, exist_ok=True)
         with open(os.path.join(self.figures_path, "epoch_average_loss_and_val_mean_dice.csv"), "w") as f:
             w = csv.writer(f)
@@ -414,6 +493,10 @@ class VSparams:
                 k = (i + 1) // self.val_interval - 1
                 m = metric_values[k] if (i + 1) % self.val_interval == 0 and 0 <= k < len(metric_values) else ""
                 w.writerow([i + 1, v, m])
+        _plot_png(os.path.join(self.figures_path, "epoch_average_loss_and_val_mean_dice.png"),
+                  [("Epoch Average Loss", [i + 1 for i in range(len(epoch_loss_values))], epoch_loss_values, "epoch"),
+                   ("Val Mean Dice", [self.val_interval * (i + 1) for i in range(len(metric_values))], metric_values,
+                    "epoch")])
 
     def load_trained_state_of_model(self, model):
         model.load_state_dict(torch.load(os.path.join(self.model_path, "best_metric_model.pth"),
@@ -421,6 +504,10 @@ class VSparams:
         return model
 
     def run_inference(self, model, data_loader):
+        """Sliding-window inference over the test set (reference VSparams.py:552-619).  On CUDA the finalise kernel
+        emits the blended probabilities, the uint8 argmax mask and the Dice sums in one pass; the results of volume
+        i are read back (one device->host copy of the mask + Dice) while volume i+1 is already running, so there
+        is no per-image host sync on the launch path."""
         logger = self.logger
         logger.info("Running inference...")
         model.eval()
@@ -432,45 +519,71 @@ class VSparams:
             model_segmentation = model
         distributed = self.world_size > 1
         if distributed:
-            import torch.distributed as dist
             from vs_seg_b200.parallel import sharded_sliding_window_inference
-            if not dist.is_initialized():
-                dist.init_process_group("nccl" if self.device.type == "cuda" else "gloo")
+        from vs_seg_b200 import sliding_window as sw
+        native = self.device.type == "cuda"
 
-        with torch.no_grad():
-            for i, data in enumerate(data_loader):
-                logger.info("starting image {}".format(i))
-                inputs = data["image"].to(self.device)
-                if distributed:
-                    outputs = sharded_sliding_window_inference(inputs, self.sliding_window_inferer_roi_size, 1,
-                                                               model_segmentation, mode="gaussian")
-                    if outputs is None:  # only rank 0 holds the blended result
-                        continue
-                else:
-                    outputs = sliding_window_inference(inputs=inputs, roi_size=self.sliding_window_inferer_roi_size,
-                                                       sw_batch_size=1, predictor=model_segmentation, mode="gaussian")
-                dice_score = self.compute_dice_score(outputs, data["label"].to(self.device))
-                dice_scores[i] = dice_score.item()
-                logger.info(f"dice_score = {dice_score.item()}")
-
-                if self.export_inferred_segmentations:
-                    logger.info("export to nifti...")
-                    nifti_data_matrix = torch.argmax(outputs, dim=1, keepdim=True)[0].to(torch.uint8)
-                    meta = {k: (v[0] if isinstance(v, (list, tuple)) else v) for k, v in data["label_meta_dict"].items()}
-                    meta["affine"] = np.squeeze(np.asarray(meta["affine"]))
-                    meta["original_affine"] = np.squeeze(np.asarray(meta["original_affine"]))
-                    folder_name = os.path.basename(os.path.dirname(meta["filename_or_obj"]))
-                    saver = NiftiSaver(output_dir=os.path.join(self.results_folder_path, "inferred_segmentations_nifti",
-                                                               folder_name), output_postfix="")
-                    saver.save(nifti_data_matrix, meta_data=meta)
-
+        def finish(i, data, mask, dice_score):
+            """Host side of one volume: log, NIfTI export, figure (mask: uint8 argmax [1,1,X,Y,Z])."""
+            mask = mask.cpu()
+            dice_scores[i] = float(dice_score)
+            logger.info(f"dice_score = {dice_scores[i]}")
+            if self.rank == 0 and self.export_inferred_segmentations:
+                logger.info("export to nifti...")
+                meta = {k: (v[0] if isinstance(v, (list, tuple)) else v) for k, v in data["label_meta_dict"].items()}
+                meta["affine"] = np.squeeze(np.asarray(meta["affine"]))
+                meta["original_affine"] = np.squeeze(np.asarray(meta["original_affine"]))
+                folder_name = os.path.basename(os.path.dirname(meta["filename_or_obj"]))
+                saver = NiftiSaver(output_dir=os.path.join(self.results_folder_path, "inferred_segmentations_nifti",
+                                                           folder_name), output_postfix="")
+                saver.save(mask[0].to(torch.uint8), meta_data=meta)
+            if self.rank == 0:
                 label = torch.squeeze(data["label"][0, 0, :, :, :])
                 slice_idx = self.get_center_of_mass_slice(label)
                 os.makedirs(self.figures_path, exist_ok=True)
                 _save_png(os.path.join(self.figures_path, "best_model_output_val" + str(i) + ".png"),
                           [data["image"][0, 0, :, :, slice_idx], data["label"][0, 0, :, :, slice_idx],
-                           torch.argmax(outputs, dim=1).detach().cpu()[0, :, :, slice_idx]])
+                           mask[0, 0, :, :, slice_idx]])
 
+        pending = None
+        with torch.no_grad():
+            for i, data in enumerate(data_loader):
+                logger.info("starting image {}".format(i))
+                inputs = data["image"].to(self.device, non_blocking=True)
+                roi = self.sliding_window_inferer_roi_size
+                if native:
+                    label = data["label"].to(torch.uint8).to(self.device, non_blocking=True)   # 1 byte per voxel
+                    if distributed:
+                        res = sharded_sliding_window_inference(inputs, roi, 1, model_segmentation, mode="gaussian",
+                                                               label=label, return_mask=True)
+                    else:
+                        acc, cnt, lows, img = sw.sliding_window_accumulate(inputs, roi, model_segmentation,
+                                                                           mode="gaussian", sw_batch_size=1)
+                        res = sw.finalize(acc, cnt, lows, img, label=label, return_mask=True)
+                    if res is None:  # only rank 0 holds the blended result
+                        continue
+                    outputs, mask, sums = res
+                    dice_dev = sw.dice_from_sums(sums).mean()
+                else:
+                    if distributed:
+                        outputs = sharded_sliding_window_inference(inputs, roi, 1, model_segmentation, mode="gaussian")
+                        if outputs is None:
+                            continue
+                    else:
+                        outputs = sliding_window_inference(inputs=inputs, roi_size=roi, sw_batch_size=1,
+                                                           predictor=model_segmentation, mode="gaussian")
+                    dice_dev = self.compute_dice_score(outputs, data["label"].to(self.device)).reshape(())
+                    mask = torch.argmax(outputs, dim=1, keepdim=True)
+                if pending is not None:   # volume i is queued: now read back volume i-1
+                    finish(*pending)
+                pending = (i, data, mask, dice_dev)
+            if pending is not None:
+                finish(*pending)
+
+        if self.rank == 0:
+            os.makedirs(self.figures_path, exist_ok=True)
+            _hist_png(os.path.join(self.figures_path, "best_model_output_dice_score_histogram.png"), dice_scores,
+                      np.arange(0, 1.01, 0.01))
         logger.info(f"all_dice_scores = {dice_scores}")
         logger.info(f"mean_dice_score = {dice_scores.mean()} +- {dice_scores.std()}")
         return dice_scores

@@ -48,6 +48,9 @@ class DiceLoss(_Loss):
         self.hardness_weight = hardness_weight
 
     def forward(self, input: torch.Tensor, target: torch.Tensor, smooth: float = 1e-5) -> torch.Tensor:
+        if input.is_cuda:   # one native reduction pass (+ one native backward pass), every constructor flag
+            from vs_seg_b200.loss_native import dice_loss_native
+            return dice_loss_native(self, input, target, smooth)
         n_pred_ch = input.shape[1]
         if self.sigmoid:
             input = torch.sigmoid(input)
@@ -127,6 +130,8 @@ class Dice_spvPA(_Loss):
     def forward(self, input, target: torch.Tensor, smooth: float = 1e-5) -> torch.Tensor:
         x, att_maps = input
         if x.is_cuda:
+            # like the reference's forward (dice_spvPA.py:250-297), which builds its two DiceLoss instances with fixed
+            # flags and ignores the constructor's include_background / to_onehot_y / ... arguments
             from vs_seg_b200.loss_native import dice_spvpa_native
             return dice_spvpa_native(x, att_maps, target, self.supervised_attention, self.hardness_weighting, smooth)
 

@@ -23,11 +23,11 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in vsseg_b200.h but not exported"
     assert sorted(lib.exported_symbols()) == names, "ctypes binding and header disagree"
-    assert lib.load().vsseg_abi_version() == 1
+    assert lib.load().vsseg_abi_version() == 2
 
 
 def test_bad_arguments_return_einval_without_gpu():
     h = lib.load()
-    code = h.vsseg_sw_finalize(None, None, None, 2, 10, None, None, None, None)
+    code = h.vsseg_sw_finalize(None, None, None, 2, 10, None, None, 0, None, None)
     assert code == 100001
     assert b"sw_finalize" in h.vsseg_last_error()

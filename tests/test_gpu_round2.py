@@ -1,0 +1,266 @@
+"""GPU parity tests added in round 2: the configuration bench.py times (128^3 windows, window groups, captured
+graph, fused gate+logits launch), the device metric path, the native standalone DiceLoss and the 2-rank NCCL path.
+
+Tolerances: 1e-3 max-abs on logits and identical argmax wherever the oracle margin exceeds 1e-4 (BASELINE.json);
+block-level kernels 5e-5 of the activation scale (split-bf16 storage, fp32 accumulation)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import loss_oracle, sw_oracle, unet_oracle  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _native_net(sd, attention=True):
+    from params.networks.nets.unet2d5_spvPA import UNet2d5_spvPA
+    net = UNet2d5_spvPA(dimensions=3, in_channels=1, out_channels=2, channels=unet_oracle.CHANNELS,
+                        strides=unet_oracle.STRIDES, kernel_sizes=unet_oracle.KERNEL_SIZES,
+                        sample_kernel_sizes=unet_oracle.SAMPLE_KERNEL_SIZES, num_res_units=2, norm="BATCH",
+                        dropout=0.1, attention_module=attention)
+    net.load_state_dict(sd, strict=True)
+    return net.to(_dev()).eval()
+
+
+# ---- fused gate + logits launch -------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,dims,cout,gate,blend,multi", [
+    (1, (6, 10, 16), 2, True, False, False),     # whole y range in one tile, no x segmentation effects
+    (2, (9, 70, 8), 2, True, True, True),        # two y tiles (halo lines), one destination view per window
+    (1, (40, 128, 32), 2, True, True, False),    # x segments + y tiles, blend into an accumulator region
+    (2, (5, 12, 24), 1, False, False, False),    # no gate, single output channel
+])
+def test_gate_logits_matches_torch(B, dims, cout, gate, blend, multi):
+    """vsseg_conv3d_gate_logits == conv3d(x * (1 + att), W, pad (1,1,0)) + bias [blended with the weight map]."""
+    import ctypes as C
+    from vs_seg_b200 import lib as vlib
+    from vs_seg_b200.engine import pack_conv_weight
+    from vs_seg_b200.tensors import Act8Buffer, f32view
+    dev = _dev()
+    lib = vlib.load()
+    g = torch.Generator().manual_seed(B * 100 + dims[1])
+    x = torch.randn((B, 32) + dims, generator=g)
+    att = torch.rand((B, 1) + dims, generator=g)
+    w = torch.randn((cout, 32, 3, 3, 1), generator=g) * 0.2
+    bias = torch.randn(cout, generator=g)
+    sw = torch.rand(dims, generator=g) + 0.1
+    buf = Act8Buffer(B, 32, *dims, dev).from_ncdhw(x.to(dev))
+    xq = buf.to_ncdhw().cpu()   # the split-bf16 rounded input both sides see
+    ref = F.conv3d(xq * (1 + att) if gate else xq, w, bias, padding=(1, 1, 0))
+    # destination: a region of a larger accumulator volume (strided view), pre-filled when blending
+    big = torch.randn((B, cout, dims[0] + 3, dims[1] + 2, dims[2] + 8), generator=g)
+    off = (2, 1, 8)
+    big_d = big.to(dev)
+    att_d, sw_d = att.to(dev), sw.to(dev)
+    wh, bh = pack_conv_weight(w, False).contiguous(), bias.clone()
+    xv = buf.view()
+    av = f32view(att_d)
+    if multi:
+        arr = (vlib.F32View * B)()
+        for b in range(B):
+            C.memmove(C.byref(arr[b]), C.byref(f32view(big_d[b:b + 1], off, dims)), C.sizeof(vlib.F32View))
+        outs, n_outs = arr, B
+    else:
+        ov = f32view(big_d, off, dims)
+        outs, n_outs = C.byref(ov), 1
+    vlib.check(lib.vsseg_conv3d_gate_logits(C.byref(xv), C.byref(av) if gate else None, wh.data_ptr(), bh.data_ptr(), cout,
+                                            outs, n_outs, sw_d.data_ptr() if blend else None,
+                                            torch.cuda.current_stream().cuda_stream), "gate_logits")
+    got = big_d.cpu()
+    region = (slice(None), slice(None)) + tuple(slice(o, o + d) for o, d in zip(off, dims))
+    want = big.clone()
+    want[region] = big[region] + sw * ref if blend else ref
+    assert torch.equal(got[:, :, :2], big[:, :, :2])   # nothing outside the region is touched
+    err = (got - want).abs().max().item()
+    assert err < 5e-5 * max(1.0, ref.abs().max().item()), err
+
+
+# ---- the timed configuration ------------------------------------------------------------------------------------
+def test_window_group_plan_equals_single_window_plan_at_128():
+    """Group-of-N plan == single-window plan, bit for bit, at the benchmark window size (line mode, x march and
+    LZ = 128 flavours of the tensor-core kernel, the multi-destination gate+logits launch)."""
+    from vs_seg_b200.tensors import f32view
+    net = _native_net(unet_oracle.seeded_state_dict(0))
+    roi = (128, 128, 128)
+    vol = torch.randn((1, 1, 224, 128, 160), generator=torch.Generator().manual_seed(5)).to(_dev())
+    starts = [(0, 0, 0), (96, 0, 32), (48, 0, 16)]
+    imap = torch.rand(roi, generator=torch.Generator().manual_seed(6)).to(_dev())
+    one = net.eval_plan(roi, batch=1)
+    grp = net.eval_plan(roi, batch=len(starts), window_levels=1)
+    acc1 = torch.zeros((1, 2, 224, 128, 160), device=_dev())
+    acc2 = torch.zeros_like(acc1)
+    for s_ in starts:
+        one.run(f32view(vol, s_, roi), f32view(acc1, s_, roi), imap.data_ptr())
+    grp.run([f32view(vol, s_, roi) for s_ in starts], [f32view(acc2, s_, roi) for s_ in starts], imap.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(acc1, acc2)
+    assert not any(st.name.endswith(".gate") and st.name.startswith("dec0") for st in grp.steps)   # no top-level gate pass
+
+
+def test_unet_eval_128_matches_oracle():
+    """Whole-network eval forward at 128^3 (the benchmark window) vs the CPU oracle: logits and attention maps."""
+    sd = unet_oracle.seeded_state_dict(0)
+    net = _native_net(sd)
+    x = torch.randn((1, 1, 128, 128, 128), generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        ref, ref_atts = unet_oracle.unet_forward(sd, x)
+        got, atts = net(x.to(_dev()))
+    got = got.cpu()
+    assert (got - ref).abs().max().item() < 1e-3
+    margin = (ref[:, 1] - ref[:, 0]).abs()
+    assert ((got.argmax(1) != ref.argmax(1)) & (margin > 1e-4)).sum().item() == 0
+    for a, r in zip(atts, ref_atts):
+        assert a.shape == r.shape and (a.cpu() - r).abs().max().item() < 1e-4
+
+
+def test_captured_graph_equals_direct_launches_and_follows_the_volume(monkeypatch):
+    """The sliding-window program: (1) graph replay == direct launches bit for bit, (2) one captured graph serves
+    another volume of the same layout (relocatable views), (3) ragged last group, (4) result vs the oracle."""
+    from vs_seg_b200 import sliding_window as sw
+    sd = unet_oracle.seeded_state_dict(4)
+    net = _native_net(sd)
+    roi = (64, 64, 16)
+    g = torch.Generator().manual_seed(21)
+    xa = torch.randn((1, 1, 96, 144, 24), generator=g)
+    xb = torch.randn((1, 1, 96, 144, 24), generator=g)
+    monkeypatch.setenv("VSSEG_SW_GROUP", "5")    # 2 x 3 x 2 = 12 windows -> groups of 5, 5, 2
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VSSEG_SW_GRAPH", mode)
+        sw._PROGRAMS.clear()
+        with torch.no_grad():
+            outs[mode] = [sw.sliding_window_inference(t.to(_dev()), roi, 1, net, mode="gaussian").cpu() for t in (xa, xb, xa)]
+        if mode == "1":
+            assert len(sw._PROGRAMS) == 1 and next(iter(sw._PROGRAMS.values())).graph is not None
+    for a, b in zip(outs["1"], outs["0"]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs["1"][0], outs["1"][2]) and not torch.equal(outs["1"][0], outs["1"][1])
+    with torch.no_grad():
+        ref = sw_oracle.sliding_window_inference(xb, roi, 1, lambda w: unet_oracle.unet_forward(sd, w)[0], mode="gaussian")
+    assert (outs["1"][1] - ref).abs().max().item() < 1e-3
+
+
+def test_sliding_window_rejects_train_mode():
+    from vs_seg_b200.sliding_window import sliding_window_inference
+    net = _native_net(unet_oracle.seeded_state_dict(4)).train()
+    with pytest.raises(RuntimeError):
+        sliding_window_inference(torch.zeros((1, 1, 64, 64, 16), device=_dev()), (64, 64, 16), 1, net, mode="gaussian")
+
+
+# ---- device metric path (VSparams.compute_dice_score, reference VSparams.py:393-408) ---------------------------
+@pytest.mark.parametrize("shape,label_dtype", [((1, 2, 16, 16, 8), torch.float32), ((2, 2, 9, 7, 5), torch.float32),
+                                                ((1, 2, 16, 16, 8), torch.uint8)])
+def test_hard_dice_matches_oracle(shape, label_dtype):
+    from vs_seg_b200.sliding_window import hard_dice
+    g = torch.Generator().manual_seed(shape[2])
+    p = torch.randn(shape, generator=g)
+    label = (torch.rand((shape[0], 1) + shape[2:], generator=g) > 0.6).float()
+    d, mask = hard_dice(p.to(_dev()), label.to(label_dtype).to(_dev()), return_mask=True)
+    assert torch.equal(mask.cpu().long()[:, 0], p.argmax(1))
+    for b in range(shape[0]):
+        assert abs(d[b].item() - loss_oracle.dice_score(p[b:b + 1], label[b:b + 1]).item()) < 1e-6
+    # empty label and empty prediction: (0 + eps) / (0 + eps) = 1
+    z = torch.zeros((1, 1) + shape[2:])
+    pz = torch.stack([torch.ones(shape[2:]), -torch.ones(shape[2:])])[None]
+    assert abs(hard_dice(pz.to(_dev()), z.to(_dev())).item() - 1.0) < 1e-12
+
+
+def test_vsparams_compute_dice_score_runs_on_the_device():
+    from params.VSparams import VSparams
+    p = VSparams.__new__(VSparams)
+    p.device = _dev()
+    g = torch.Generator().manual_seed(3)
+    prob = torch.randn((1, 2, 32, 32, 8), generator=g)
+    label = (torch.rand((1, 1, 32, 32, 8), generator=g) > 0.5).float()
+    got = p.compute_dice_score(prob.to(_dev()), label.to(_dev()))
+    assert got.shape == (1, 1) and got.is_cuda
+    assert abs(got.item() - loss_oracle.dice_score(prob, label).item()) < 1e-6
+
+
+def test_finalize_uint8_label_and_vector_tail():
+    from vs_seg_b200.sliding_window import dice_from_sums, finalize
+    dev = _dev()
+    g = torch.Generator().manual_seed(2)
+    for dims in ((16, 16, 8), (5, 7, 3)):   # n % 4 == 0 (128-bit path) and an odd size (scalar path)
+        acc = torch.randn((1, 2) + dims, generator=g)
+        cnt = torch.rand(dims, generator=g) + 0.5
+        label = torch.rand((1, 1) + dims, generator=g) > 0.7
+        out, mask, sums = finalize(acc.to(dev), cnt.to(dev), [0, 0, 0], list(dims), label=label.to(torch.uint8).to(dev),
+                                   return_mask=True)
+        ref = acc / cnt
+        assert torch.equal(out.cpu(), ref)
+        assert torch.equal(mask.cpu().long()[:, 0], ref.argmax(1))
+        assert abs(dice_from_sums(sums)[0].item() - loss_oracle.dice_score(ref, label.float()).item()) < 1e-6
+
+
+# ---- native standalone DiceLoss (reference dice_spvPA.py:90-167) -----------------------------------------------
+DICE_FLAG_CASES = [
+    dict(),                                                         # single channel, the attention-map form
+    dict(to_onehot_y=True, softmax=True),                           # the logits form
+    dict(to_onehot_y=True, softmax=True, include_background=False),
+    dict(sigmoid=True, squared_pred=True),
+    dict(to_onehot_y=True, softmax=True, jaccard=True, reduction="sum"),
+    dict(to_onehot_y=True, softmax=True, reduction="none", weighted=True),
+]
+
+
+@pytest.mark.parametrize("flags", DICE_FLAG_CASES)
+def test_dice_loss_native_matches_cpu_module(flags):
+    """DiceLoss on CUDA tensors (native reduction + native backward) vs the same module on the CPU (the torch
+    composition that follows the reference line by line and is pinned by tests/test_oracle_golden.py)."""
+    from params.losses.dice_spvPA import DiceLoss
+    flags = dict(flags)
+    weighted = flags.pop("weighted", False)
+    C = 2 if flags.get("softmax") or flags.get("to_onehot_y") else 1
+    shape = (2, C, 12, 10, 8)
+    g = torch.Generator().manual_seed(len(flags) + C)
+    x = torch.randn(shape, generator=g)
+    if C == 1 and not flags.get("sigmoid"):
+        x = torch.rand(shape, generator=g)
+    t = (torch.rand((2, 1) + shape[2:], generator=g) > 0.6).float()
+    if not flags.get("to_onehot_y") and C > 1:
+        t = loss_oracle.one_hot(t, C)
+    w = torch.rand(shape, generator=g) + 0.5 if weighted else None
+    xc = x.clone().requires_grad_(True)
+    ref = DiceLoss(hardness_weight=w, **flags)(xc, t)
+    ref.sum().backward()
+    xg = x.to(_dev()).requires_grad_(True)
+    got = DiceLoss(hardness_weight=w.to(_dev()) if w is not None else None, **flags)(xg, t.to(_dev()))
+    got.sum().backward()
+    assert got.shape == ref.shape
+    assert (got.cpu() - ref).abs().max().item() < 2e-6
+    assert (xg.grad.cpu() - xc.grad).abs().max().item() < 1e-6 + 1e-4 * xc.grad.abs().max().item()
+    if C == 1 and not flags:
+        assert abs(got.item() - loss_oracle.dice_loss(x, t).item()) < 2e-6
+
+
+def test_dice_loss_native_shape_mismatch_raises():
+    from params.losses.dice_spvPA import DiceLoss
+    with pytest.raises(AssertionError):
+        DiceLoss()(torch.zeros(1, 1, 4, 4, 4, device=_dev()), torch.zeros(1, 1, 4, 4, 5, device=_dev()))
+
+
+# ---- two ranks over NCCL ----------------------------------------------------------------------------------------
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_two_rank_nccl_sharded_inference_equals_one_gpu(tmp_path):
+    """Windows sharded over 2 NCCL ranks + reduce == the 1-GPU result (sum order differs: 1e-5) and the oracle."""
+    out = str(tmp_path / "r0.pt")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(ROOT, "tests", "nccl_sw_worker.py"), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = torch.load(out)
+    assert res["err_vs_single"] < 1e-5, res
+    assert res["err_vs_oracle"] < 1e-3 and res["flips"] == 0, res
+    assert res["mask_equal"] and abs(res["dice_sharded"] - res["dice_single"]) < 1e-4, res

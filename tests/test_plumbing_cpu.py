@@ -86,6 +86,11 @@ def test_vsparams_train_and_inference_recipe_on_cpu(tmp_path, monkeypatch):
     assert os.path.isfile(out)
     seg, _ = dataio.read_nifti(out)
     assert seg.shape == (48, 56, 12) and set(np.unique(seg)) <= {0, 1}
+    # figures of the reference (VSparams.py:530-545, :596-616), drawn with PIL
+    for f in ("epoch_average_loss_and_val_mean_dice.png", "best_model_output_dice_score_histogram.png",
+              "best_model_output_val0.png", "best_model_output_val1.png", "check_validation_image_and_label.png"):
+        assert os.path.getsize(os.path.join(p.figures_path, f)) > 0
+    assert os.path.isfile(os.path.join(root, "params", "split_TCIA.csv"))   # the default of --split
     for h in list(p.logger.handlers):
         p.logger.removeHandler(h)
 
@@ -110,3 +115,28 @@ def test_fused_adam_on_cpu_is_torch_adam():
     for p, q in zip(a, b):
         assert torch.equal(p, q)
     assert oa.flat_grads() == []
+
+
+def test_nifti_saver_restores_the_original_orientation(tmp_path):
+    """NiftiSaver must undo Orientationd(RAS) before writing under the file's original affine (reference
+    VSparams.py:582-594 passes affine AND original_affine to MONAI's NiftiSaver): LPS-ordered files (negative
+    diagonal, as Slicer exports the VS data) and permuted axes round-trip voxel for voxel."""
+    import numpy as np
+    from vs_seg_b200 import dataio
+    rng = np.random.RandomState(0)
+    vol = (rng.rand(8, 6, 4) > 0.5).astype(np.uint8)
+    affines = [np.array([[-0.4, 0, 0, 50.], [0, -0.4, 0, 60.], [0, 0, 1.5, -20.], [0, 0, 0, 1]]),
+               np.array([[0, -0.5, 0, 10.], [0.7, 0, 0, 5.], [0, 0, -2.0, 3.], [0, 0, 0, 1]]),
+               np.diag([1.0, 1.0, 1.0, 1.0])]
+    for k, aff in enumerate(affines):
+        src = str(tmp_path / f"case{k}.nii.gz")
+        dataio.write_nifti(src, vol, aff)
+        d = dataio.LoadNiftid(keys=["label"])({"label": src})
+        d = dataio.Orientationd(keys=["label"])(dataio.AddChanneld(keys=["label"])(d))
+        ras = d["label_meta_dict"]["affine"]
+        assert all(ras[i, i] > 0 for i in range(3))                     # the network sees RAS data
+        out = dataio.NiftiSaver(output_dir=str(tmp_path / "out"), output_postfix="").save(
+            d["label"], meta_data=d["label_meta_dict"])
+        back, aff_back = dataio.read_nifti(out)
+        assert np.array_equal(back, vol)
+        assert np.allclose(aff_back, aff, atol=1e-5)

@@ -74,6 +74,16 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     return v >= 0.f ? v : v * slope;
 }
 
+// base pointer of an fp32 view: relocatable views (vsseg_f32view.indirect) keep a byte offset in `ptr` and the base
+// address in a device cell, read here at run time (one captured graph serves every volume)
+__device__ __forceinline__ float* f32_base(const vsseg_f32view& v) {
+    if (v.indirect)
+        return reinterpret_cast<float*>(__ldg(reinterpret_cast<const long long*>(v.indirect)) + reinterpret_cast<long long>(v.ptr));
+    return v.ptr;
+}
+inline bool f32_ok(const vsseg_f32view* v) { return v && (v->ptr || v->indirect); }
+inline bool f32_direct(const vsseg_f32view* v) { return v && v->ptr && !v->indirect; }
+
 // element offset of (b, cg, x, y, z) group start in an act8 plane
 __device__ __forceinline__ int64_t act8_off(int64_t bstride, int X, int Y, int Z, int b, int cg, int x, int y, int z) {
     return (int64_t)b * bstride + ((((int64_t)cg * X + x) * Y + y) * Z + z) * 8;

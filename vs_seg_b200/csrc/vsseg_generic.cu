@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) conv_act8_kernel(const ConvArgs a) {
         if (!vok[j]) continue;
         float rsrc = 0.f;
         if (a.res_mode == 2)
-            rsrc = a.rsrc.ptr[vb[j] * a.rsrc.sb + vx[j] * a.rsrc.sx + vy[j] * a.rsrc.sy + vz[j] * a.rsrc.sz];
+            rsrc = f32_base(a.rsrc)[vb[j] * a.rsrc.sb + vx[j] * a.rsrc.sx + vy[j] * a.rsrc.sy + vz[j] * a.rsrc.sz];
 #pragma unroll
         for (int g8 = 0; g8 < CO_T / 8; ++g8) {
             const int c0 = co0 + g8 * 8;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(128) conv_cin1_kernel(const Cin1Args a) {
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-    const float* src = a.in.ptr + (int64_t)b * a.in.sb;
+    const float* src = f32_base(a.in) + (int64_t)b * a.in.sb;
     int tap = 0;
     for (int tx = 0; tx < a.g.kx; ++tx)
         for (int ty = 0; ty < a.g.ky; ++ty) {
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(128) conv_cin1_k331_kernel(const Cin1Args a) {
     for (int v = 0; v < CIN1_YB; ++v)
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[v][c] = 0.f;
-    const float* src = a.in.ptr + (int64_t)b * a.in.sb + (int64_t)z * a.in.sz;
+    const float* src = f32_base(a.in) + (int64_t)b * a.in.sb + (int64_t)z * a.in.sz;
 #pragma unroll
     for (int tx = 0; tx < 3; ++tx) {
         const int xi = x - 1 + tx;
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(128) conv_smallcout_kernel(const SmallCoutArgs
 #pragma unroll
     for (int c = 0; c < COUT; ++c) {
         float r = apply_act(acc[c] + __ldg(a.bias + c), a.act, a.slope);
-        float* o = a.out.ptr + b * a.out.sb + c * a.out.sc + x * a.out.sx + y * a.out.sy + z * a.out.sz;
+        float* o = f32_base(a.out) + b * a.out.sb + c * a.out.sc + x * a.out.sx + y * a.out.sy + z * a.out.sz;
         if (a.sw_weight)
             *o += sw * r;
         else
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(256) att_gate_kernel(vsseg_act8 x, vsseg_f32vi
         int z = (int)(v % x.Z);
         int y = (int)((v / x.Z) % x.Y);
         int xx = (int)(v / ((int64_t)x.Z * x.Y));
-        float g = 1.0f + __ldg(att.ptr + b * att.sb + xx * att.sx + y * att.sy + z * att.sz);
+        float g = 1.0f + __ldg(f32_base(att) + b * att.sb + xx * att.sx + y * att.sy + z * att.sz);
         const __nv_bfloat16* p = xh + (int64_t)b * x.batch_stride + ((int64_t)cg * nvox + v) * 8;
         float f[8];
         unpack8(ldg128(p), ldg128(p + x.lo_offset), f);
@@ -467,30 +467,72 @@ __global__ void __launch_bounds__(256) att_gate_kernel(vsseg_act8 x, vsseg_f32vi
 // -------------------------------------------------------------------------------------------
 // sliding-window finalise
 // -------------------------------------------------------------------------------------------
+// 4 voxels per thread: 128-bit loads of every accumulator channel and of the weight-sum map, 128-bit store of the
+// probabilities, 32-bit store of the mask (C <= 8 channels stay in registers)
+template <typename LabelT, bool VEC>
 __global__ void __launch_bounds__(256) sw_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ cnt,
                                                           float* __restrict__ out, int C, int64_t n,
-                                                          uint8_t* __restrict__ mask, const float* __restrict__ label,
+                                                          uint8_t* __restrict__ mask, const LabelT* __restrict__ label,
                                                           double* sums) {
+    constexpr int V = VEC ? 4 : 1;
     float s_i = 0.f, s_l = 0.f, s_p = 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float cv = cnt[i];
-        float best = 0.f;
-        int arg = 0;
-        for (int c = 0; c < C; ++c) {
-            float p = acc[c * n + i] / cv;
-            if (out) out[c * n + i] = p;
-            if (c == 0 || p > best) {  // first maximum wins, as torch.argmax
-                best = p;
-                arg = c;
+    const int64_t nv = n / V;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+        float inv[V], best[V];
+        int arg[V];
+        if (cnt) {
+            if constexpr (VEC) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cnt) + i);
+                inv[0] = c4.x; inv[1] = c4.y; inv[2] = c4.z; inv[3] = c4.w;
+            } else {
+                inv[0] = cnt[i];
             }
         }
-        if (mask) mask[i] = (uint8_t)arg;
+        for (int c = 0; c < C; ++c) {
+            float p[V];
+            if constexpr (VEC) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(acc + c * n) + i);
+                p[0] = a4.x; p[1] = a4.y; p[2] = a4.z; p[3] = a4.w;
+            } else {
+                p[0] = acc[c * n + i];
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                if (cnt) p[k] = p[k] / inv[k];   // true division, as MONAI's out / count
+                if (c == 0 || p[k] > best[k]) {  // first maximum wins, as torch.argmax
+                    best[k] = p[k];
+                    arg[k] = c;
+                }
+            }
+            if (out) {
+                if constexpr (VEC) reinterpret_cast<float4*>(out + c * n)[i] = make_float4(p[0], p[1], p[2], p[3]);
+                else out[c * n + i] = p[0];
+            }
+        }
+        if (mask) {
+            if constexpr (VEC) reinterpret_cast<uchar4*>(mask)[i] = make_uchar4((uint8_t)arg[0], (uint8_t)arg[1], (uint8_t)arg[2], (uint8_t)arg[3]);
+            else mask[i] = (uint8_t)arg[0];
+        }
         if (label) {
-            const float lb = label[i];
-            const float pr = arg == 1 ? 1.f : 0.f;
-            s_i += pr * lb;
-            s_l += lb;
-            s_p += pr;
+            float lb[V];
+            if constexpr (VEC) {
+                if constexpr (sizeof(LabelT) == 4) {
+                    const float4 l4 = __ldg(reinterpret_cast<const float4*>(label) + i);
+                    lb[0] = l4.x; lb[1] = l4.y; lb[2] = l4.z; lb[3] = l4.w;
+                } else {
+                    const uchar4 l4 = __ldg(reinterpret_cast<const uchar4*>(label) + i);
+                    lb[0] = l4.x; lb[1] = l4.y; lb[2] = l4.z; lb[3] = l4.w;
+                }
+            } else {
+                lb[0] = (float)label[i];
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float pr = arg[k] == 1 ? 1.f : 0.f;
+                s_i += pr * lb[k];
+                s_l += lb[k];
+                s_p += pr;
+            }
         }
     }
     if (label && sums) {
@@ -543,7 +585,7 @@ int vsseg_device_sm_count(int device, int* sm_count_host) {
 }
 
 int vsseg_pack_act8(const vsseg_f32view* src, const vsseg_act8* dst, void* stream) {
-    VSSEG_REQUIRE(src && src->ptr && act8_ok(dst), "pack_act8: bad tensor descriptor");
+    VSSEG_REQUIRE(f32_direct(src) && act8_ok(dst), "pack_act8: bad tensor descriptor");
     VSSEG_REQUIRE(src->C == dst->C && src->B == dst->B && src->X == dst->X && src->Y == dst->Y && src->Z == dst->Z,
                   "pack_act8: shape mismatch");
     int64_t total = (int64_t)dst->B * (dst->C / 8) * dst->X * dst->Y * dst->Z;
@@ -552,7 +594,7 @@ int vsseg_pack_act8(const vsseg_f32view* src, const vsseg_act8* dst, void* strea
 }
 
 int vsseg_unpack_act8(const vsseg_act8* src, const vsseg_f32view* dst, void* stream) {
-    VSSEG_REQUIRE(dst && dst->ptr && act8_ok(src), "unpack_act8: bad tensor descriptor");
+    VSSEG_REQUIRE(f32_direct(dst) && act8_ok(src), "unpack_act8: bad tensor descriptor");
     VSSEG_REQUIRE(src->C == dst->C && src->B == dst->B && src->X == dst->X && src->Y == dst->Y && src->Z == dst->Z,
                   "unpack_act8: shape mismatch");
     int64_t total = (int64_t)src->B * (src->C / 8) * src->X * src->Y * src->Z;
@@ -601,7 +643,7 @@ int vsseg_conv3d_act8(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
         a.res_mode = 1;
         a.res = *res_act8;
     } else if (res_src) {
-        VSSEG_REQUIRE(res_src->ptr && res_w && res_b, "conv3d_act8: NULL cin1 residual");
+        VSSEG_REQUIRE(f32_ok(res_src) && res_w && res_b, "conv3d_act8: NULL cin1 residual");
         a.res_mode = 2;
         a.rsrc = *res_src;
         a.res_w = res_w;
@@ -623,7 +665,7 @@ int vsseg_conv3d_act8(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
 
 int vsseg_conv3d_cin1(const vsseg_f32view* in, const vsseg_act8* out, const vsseg_conv_geom* g, const float* w,
                       const vsseg_epilogue* ep, void* stream) {
-    VSSEG_REQUIRE(in && in->ptr && act8_ok(out), "conv3d_cin1: bad tensor descriptor");
+    VSSEG_REQUIRE(f32_ok(in) && act8_ok(out), "conv3d_cin1: bad tensor descriptor");
     if (int e = check_geom(g, "conv3d_cin1")) return e;
     VSSEG_REQUIRE(g->sx == 1 && g->sy == 1 && g->sz == 1 && !g->transposed, "conv3d_cin1: stride-1 conv only");
     VSSEG_REQUIRE(out->C == 16, "conv3d_cin1: Cout must be 16 (got %d)", out->C);
@@ -646,7 +688,7 @@ int vsseg_conv3d_cin1(const vsseg_f32view* in, const vsseg_act8* out, const vsse
 
 int vsseg_conv3d_smallcout(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const float* w,
                            const float* bias, int32_t act, float slope, const float* sw_weight, void* stream) {
-    VSSEG_REQUIRE(act8_ok(in) && out && out->ptr, "conv3d_smallcout: bad tensor descriptor");
+    VSSEG_REQUIRE(act8_ok(in) && f32_ok(out), "conv3d_smallcout: bad tensor descriptor");
     if (int e = check_geom(g, "conv3d_smallcout")) return e;
     VSSEG_REQUIRE(g->sx == 1 && g->sy == 1 && g->sz == 1 && !g->transposed, "conv3d_smallcout: stride-1 conv only");
     VSSEG_REQUIRE(out->C == 1 || out->C == 2, "conv3d_smallcout: Cout must be 1 or 2");
@@ -667,7 +709,7 @@ int vsseg_conv3d_smallcout(const vsseg_act8* in, const vsseg_f32view* out, const
 }
 
 int vsseg_att_gate(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_act8* out, void* stream) {
-    VSSEG_REQUIRE(act8_ok(x) && act8_ok(out) && att && att->ptr, "att_gate: bad tensor descriptor");
+    VSSEG_REQUIRE(act8_ok(x) && act8_ok(out) && f32_ok(att), "att_gate: bad tensor descriptor");
     VSSEG_REQUIRE(x->C == out->C && x->B == out->B && x->X == out->X && x->Y == out->Y && x->Z == out->Z &&
                       att->B == x->B && att->X == x->X && att->Y == x->Y && att->Z == x->Z,
                   "att_gate: shape mismatch");
@@ -677,10 +719,22 @@ int vsseg_att_gate(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_ac
 }
 
 int vsseg_sw_finalize(const float* acc, const float* cnt, float* out, int32_t C, int64_t n, uint8_t* mask,
-                      const float* label, double* sums, void* stream) {
-    VSSEG_REQUIRE(acc && cnt && C >= 1 && n > 0, "sw_finalize: bad arguments");
+                      const void* label, int32_t label_u8, double* sums, void* stream) {
+    VSSEG_REQUIRE(acc && C >= 1 && n > 0, "sw_finalize: bad arguments");
     VSSEG_REQUIRE(!label || sums, "sw_finalize: label given without sums");
-    sw_finalize_kernel<<<grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(acc, cnt, out, C, n, mask, label, sums);
+    auto al = [](const void* p, size_t a) { return ((uintptr_t)p % a) == 0; };
+    const bool vec = n % 4 == 0 && al(acc, 16) && al(cnt, 16) && al(out, 16) && al(mask, 4) && al(label, label_u8 ? 4 : 16);
+    const int grid = grid_for(vec ? n / 4 : n, 256, 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (label_u8) {
+        const uint8_t* lb = (const uint8_t*)label;
+        if (vec) sw_finalize_kernel<uint8_t, true><<<grid, 256, 0, st>>>(acc, cnt, out, C, n, mask, lb, sums);
+        else sw_finalize_kernel<uint8_t, false><<<grid, 256, 0, st>>>(acc, cnt, out, C, n, mask, lb, sums);
+    } else {
+        const float* lb = (const float*)label;
+        if (vec) sw_finalize_kernel<float, true><<<grid, 256, 0, st>>>(acc, cnt, out, C, n, mask, lb, sums);
+        else sw_finalize_kernel<float, false><<<grid, 256, 0, st>>>(acc, cnt, out, C, n, mask, lb, sums);
+    }
     return check_launch("sw_finalize");
 }
 

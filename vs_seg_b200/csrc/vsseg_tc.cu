@@ -163,6 +163,8 @@ struct EpiCtx {
     int b, ox, my0, mz0, ly, zz, co0, nreal;
     bool sc, sig;
     float slope;
+    const float* rsrc_p;   // base pointers of the fp32 views (relocatable views resolved once per thread)
+    float* outf_p;
 };
 template <bool SC, int RM>
 struct EpiUnit {
@@ -204,7 +206,7 @@ __device__ __forceinline__ void epi_load(const EpiCtx& X, EpiUnit<SC, RM>& U) {
         }
       }
     } else if constexpr (RM == 2) {
-        if (U.valid) U.rsrc = __ldg(a.rsrc.ptr + X.b * a.rsrc.sb + X.ox * a.rsrc.sx + U.oy * a.rsrc.sy + U.oz * a.rsrc.sz);
+        if (U.valid) U.rsrc = __ldg(X.rsrc_p + X.b * a.rsrc.sb + X.ox * a.rsrc.sx + U.oy * a.rsrc.sy + U.oz * a.rsrc.sz);
     }
 }
 
@@ -227,7 +229,7 @@ __device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) 
             if (a.two_pass) raw += __uint_as_float(a.cout == 1 ? U.v[q + 1] : U.v[q + 2]);   // + hi*lo partial sums
             float f = raw * ep_c[q] + ep_c[256 + q];
             f = apply_act(f, a.ep.act, X.slope);
-            float* o = a.outf.ptr + X.b * a.outf.sb + q * a.outf.sc + X.ox * a.outf.sx + U.oy * a.outf.sy + U.oz * a.outf.sz;
+            float* o = X.outf_p + X.b * a.outf.sb + q * a.outf.sc + X.ox * a.outf.sx + U.oy * a.outf.sy + U.oz * a.outf.sz;
             if (a.sw_weight) *o += sw * f;
             else *o = f;
             if constexpr (OM == 2) {
@@ -615,6 +617,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         const float slope = a.ep.slope;
         const int64_t lo_out = a.out.lo_offset, lo_res = a.res.lo_offset;
         int rowbase = 0;
+        const float* const rsrc_p = RM == 2 ? f32_base(a.rsrc) : nullptr;
+        float* const outf_p = OM >= 1 ? f32_base(a.outf) : nullptr;
         long long t_wait = 0, t_beg = clock64();
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const TcTile T = decode_tile(a, tile);
@@ -636,7 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 if (a.dbg) t_wait += clock64() - t0;
                 // units = (accumulator ai, 16-column chunk c), dealt to the quadrant's warps like the zeroing below
                 // (two units in flight per thread were tried: the extra registers spill and it is slower)
-                EpiCtx X{a, ep_c, tacc, row_cols, row_off, cgs, lo_out, lo_res, out_b, res_b, b, ox, my0, mz0, ly, zz, co0, nreal, sc, sig, slope};
+                EpiCtx X{a, ep_c, tacc, row_cols, row_off, cgs, lo_out, lo_res, out_b, res_b, b, ox, my0, mz0, ly, zz, co0, nreal, sc, sig, slope, rsrc_p, outf_p};
                 int ai = 0, c = esub;
                 while (c >= n16) { c -= n16; ++ai; }
                 while (ai < a.nacc) {
@@ -806,8 +810,13 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
         if (in->X % g->sx || in->Y % g->sy || in->Z % g->sz) return false;
         Xm = out->X; Ym = out->Y; Zm = out->Z;
     }
-    const int LZ = Zm >= 128 ? 128 : Zm;
-    if (Zm % LZ || 128 % LZ || LZ < 8) return false;
+    // z extent of the M tile: the largest power of two (<= 128) that divides the z extent of the M grid, so any
+    // crop tiles (Z = 40 -> 8, 96 -> 32, 160 -> 32; the coarse levels of shallow crops run with LZ = 4, 2, 1 and
+    // LY = 32..128 lines per tile, rows beyond the y extent masked)
+    static const int lz_min = getenv("VSSEG_TC_LZ_MIN") ? atoi(getenv("VSSEG_TC_LZ_MIN")) : 1;
+    int LZ = 128;
+    while (LZ > 1 && Zm % LZ) LZ >>= 1;
+    if (LZ < lz_min) return false;
     const int LY = 128 / LZ;
     const int64_t cgs = (int64_t)in->X * in->Y * in->Z * 8;
     if (in->lo_offset % cgs || in->batch_stride % cgs) return false;
@@ -873,6 +882,7 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             else { nbox = KZ; BY = YT * LY + 2 * hy; BZ = LZ; }
             if (!line && (BY * (strided ? g->sy : 1) > 256 || BZ * (strided ? g->sz : 1) > 256)) break;
             const size_t box_bytes = (size_t)2 * BY * BZ * 16;
+            if (!line && nbox > 1 && box_bytes % 128) continue;   // every TMA box must land 128-byte aligned (tiny LZ)
             const size_t a_plane = round_up((int)(nbox * box_bytes), 128);
             double mma_cyc = 0;
             {
@@ -1208,10 +1218,10 @@ int vsseg_conv3d_tc_suggest_split(const vsseg_act8* in, const vsseg_act8* out, c
 
 static int tc_f32out(const vsseg_act8* in, const vsseg_f32view* out, const vsseg_conv_geom* g, const void* w_packed,
                      const vsseg_epilogue* ep, const float* sw_weight, void* stream, int two_pass, const vsseg_act8* gate = nullptr) {
-    VSSEG_REQUIRE(in && out && out->ptr && out->C >= 1 && out->C <= 2, "conv3d_tc_f32out: Cout must be 1 or 2");
+    VSSEG_REQUIRE(in && f32_ok(out) && out->C >= 1 && out->C <= 2, "conv3d_tc_f32out: Cout must be 1 or 2");
     // the plan only needs the output extents: describe the planar output as a 16-channel act8 tensor
     vsseg_act8 o16{};
-    o16.hi = out->ptr; o16.B = out->B; o16.C = 16; o16.X = out->X; o16.Y = out->Y; o16.Z = out->Z;
+    o16.hi = (void*)16; o16.B = out->B; o16.C = 16; o16.X = out->X; o16.Y = out->Y; o16.Z = out->Z;
     static TcPlan P;
     VSSEG_REQUIRE(g && !g->transposed && g->sx == 1 && g->sy == 1 && g->sz == 1 && make_plan(in, &o16, g, 1, nullptr, &P),
                   "conv3d_tc_f32out: unsupported shape (stride-1 convs covered by vsseg_conv3d_tc_supported)");
@@ -1297,7 +1307,7 @@ int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_con
         a.res_mode = 1;
         a.res = *res_act8;
     } else if (res_src) {
-        VSSEG_REQUIRE(res_src->ptr && res_w && res_b, "conv3d_tc: NULL cin1 residual");
+        VSSEG_REQUIRE(f32_ok(res_src) && res_w && res_b, "conv3d_tc: NULL cin1 residual");
         a.res_mode = 2;
         a.rsrc = *res_src; a.res_w = res_w; a.res_b = res_b;
     }

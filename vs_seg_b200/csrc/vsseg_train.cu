@@ -757,7 +757,7 @@ int vsseg_conv3d_wgrad(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_co
 
 int vsseg_conv3d_cin1_wgrad(const vsseg_f32view* src, const vsseg_act8* dc, const vsseg_conv_geom* g, float* dw, float* dbias,
                             void* stream) {
-    VSSEG_REQUIRE(src && src->ptr && a8ok(dc) && g && dw, "cin1_wgrad: bad arguments");
+    VSSEG_REQUIRE(f32_direct(src) && a8ok(dc) && g && dw, "cin1_wgrad: bad arguments");
     VSSEG_REQUIRE(!g->transposed && g->sx == 1 && g->sy == 1 && g->sz == 1, "cin1_wgrad: stride-1 conv only");
     Cin1WgradArgs a{*src, *dc, *g, dw, dbias};
     const int64_t total = (int64_t)dc->B * dc->X * dc->Y * dc->Z;
@@ -772,9 +772,9 @@ int vsseg_conv3d_cin1_wgrad(const vsseg_f32view* src, const vsseg_act8* dc, cons
 
 int vsseg_conv3d_smallcout_bwd(const vsseg_act8* x, const vsseg_f32view* dy, const vsseg_f32view* y, const vsseg_conv_geom* g,
                                const float* w, int32_t sigmoid, const vsseg_act8* dx, float* dw, float* dbias, void* stream) {
-    VSSEG_REQUIRE(a8ok(x) && dy && dy->ptr && g && w, "smallcout_bwd: bad arguments");
+    VSSEG_REQUIRE(a8ok(x) && f32_direct(dy) && g && w, "smallcout_bwd: bad arguments");
     VSSEG_REQUIRE(dy->C == 1 || dy->C == 2, "smallcout_bwd: Cout must be 1 or 2");
-    VSSEG_REQUIRE(!sigmoid || (y && y->ptr), "smallcout_bwd: sigmoid backward needs the forward output");
+    VSSEG_REQUIRE(!sigmoid || f32_direct(y), "smallcout_bwd: sigmoid backward needs the forward output");
     VSSEG_REQUIRE(!g->transposed && g->sx == 1 && g->sy == 1 && g->sz == 1, "smallcout_bwd: stride-1 conv only");
     SmallBwdArgs a{*x, dx ? *dx : *x, *dy, y ? *y : *dy, *g, w, dw, dbias, sigmoid};
     const int taps = g->kx * g->ky * g->kz;
@@ -813,7 +813,7 @@ int vsseg_conv3d_smallcout_bwd(const vsseg_act8* x, const vsseg_f32view* dy, con
 
 int vsseg_att_gate_bwd(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_act8* dg, const vsseg_act8* dx,
                        const vsseg_f32view* datt, int32_t accumulate_dx, void* stream) {
-    VSSEG_REQUIRE(a8ok(x) && a8ok(dg) && a8ok(dx) && same_shape(x, dg) && same_shape(x, dx) && att && att->ptr && datt && datt->ptr,
+    VSSEG_REQUIRE(a8ok(x) && a8ok(dg) && a8ok(dx) && same_shape(x, dg) && same_shape(x, dx) && f32_direct(att) && f32_direct(datt),
                   "att_gate_bwd: bad arguments");
     const int64_t total = (int64_t)x->B * x->X * x->Y * x->Z;
     gate_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, *att, *dg, *dx, *datt, accumulate_dx);

@@ -305,6 +305,10 @@ class NiftiSaver:
         self.output_dir, self.output_postfix, self.output_ext = output_dir, output_postfix, output_ext
 
     def save(self, data, meta_data=None):
+        """MONAI's NiftiSaver (reference VSparams.py:582-594) receives both `affine` (of the array after
+        Orientationd) and `original_affine` (of the file on disk) and writes the data back in the ORIGINAL
+        orientation.  Here the axis permutation and flips implied by the two affines are undone exactly; if they
+        differ by more than that (a resampling would be needed) the array is written with its own `affine`."""
         arr = data.detach().cpu().numpy() if torch.is_tensor(data) else np.asarray(data)
         name = os.path.basename(str(meta_data["filename_or_obj"])) if meta_data else "output"
         for ext in (".nii.gz", ".nii"):
@@ -312,9 +316,35 @@ class NiftiSaver:
                 name = name[:-len(ext)]
         post = f"_{self.output_postfix}" if self.output_postfix else ""
         path = os.path.join(self.output_dir, name, name + post + self.output_ext)
-        affine = np.asarray(meta_data.get("original_affine", meta_data.get("affine"))) if meta_data else None
-        write_nifti(path, np.squeeze(arr, 0) if arr.ndim == 4 and arr.shape[0] == 1 else arr, affine)
+        arr = np.squeeze(arr, 0) if arr.ndim == 4 and arr.shape[0] == 1 else arr
+        affine = None
+        if meta_data:
+            cur = meta_data.get("affine")
+            orig = meta_data.get("original_affine")
+            affine = np.asarray(cur if cur is not None else orig, dtype=np.float64)
+            if cur is not None and orig is not None and arr.ndim == 3:
+                arr, affine = _to_original_orientation(arr, np.asarray(cur, dtype=np.float64),
+                                                       np.asarray(orig, dtype=np.float64))
+        write_nifti(path, arr, affine)
         return path
+
+
+def _to_original_orientation(arr, affine, original_affine, tol=1e-3):
+    """Undo the axis permutation / flips between `affine` (describes arr) and `original_affine`.
+    Returns (array in the original voxel order, the affine that describes it)."""
+    T = np.linalg.inv(original_affine) @ affine   # current voxel index -> original voxel index
+    M = T[:3, :3]
+    src = [int(np.argmax(np.abs(M[o, :]))) for o in range(3)]   # current axis that runs along original axis o
+    P = np.zeros((3, 3))
+    for o, c in enumerate(src):
+        P[o, c] = np.sign(M[o, c])
+    if sorted(src) != [0, 1, 2] or np.abs(M - P).max() > tol:
+        return arr, affine   # not a pure reorientation: keep the array as it is, described by its own affine
+    out = np.transpose(arr, src)
+    for o, c in enumerate(src):
+        if M[o, c] < 0:
+            out = np.flip(out, axis=o)
+    return np.ascontiguousarray(out), original_affine
 
 
 # ---- synthetic cases (no dataset can be downloaded here) --------------------------------------------

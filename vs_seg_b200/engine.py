@@ -195,7 +195,8 @@ class UNetEvalPlan:
         self.window_levels = max(0, min(int(window_levels), len(channels) - 1)) if self.B > 1 else 0
         nview = self.B if self.window_levels else 1
         self.srcs = [_lib.F32View() for _ in range(nview)]
-        self.dsts = [_lib.F32View() for _ in range(nview)]
+        self._dst_arr = (_lib.F32View * nview)()   # contiguous: one launch can take every window's destination
+        self.dsts = [self._dst_arr[i] for i in range(nview)]
         self.src, self.dst = self.srcs[0], self.dsts[0]
         self._bs = (0, self.B)   # batch slice the step being emitted works on
         self.sw_weight = C.c_void_p(None)
@@ -256,7 +257,10 @@ class UNetEvalPlan:
                     sc_tail = (sc_p, w2.data_ptr(), b2.data_ptr())
                     self._keep.append(sc_src)
                     f2, n2 = _conv_cost(sc_src, dst, (1, 1, 1), False, sc_src.C, cout)
-                    fl, nb = fl + f2, nb + n2 - 4 * _nvox(dst) * cout
+                    # the output is written once; a decoder unit's shortcut reads the SAME tensor as its conv
+                    # (one subunit), which SURVEY.md §8d counts once
+                    same = sc_src.hi == src.hi and sc_src.C == src.C
+                    fl, nb = fl + f2, nb + n2 - 4 * _nvox(dst) * cout - (4 * _nvox(sc_src) * sc_src.C if same else 0)
                 args = (C.byref(src), C.byref(dst), C.byref(g), w.data_ptr(), ns, C.byref(ep)) + tail + sc_tail
                 self.steps.append(_Step(name, self.lib.vsseg_conv3d_tc, args, fl, nb, kind="tcgen05"))
                 return fused
@@ -326,6 +330,35 @@ class UNetEvalPlan:
                                  slope, sw_weight), fl, nb))
         return False
 
+    def _gate_logits_ok(self, buf, k):
+        return (os.environ.get("VSSEG_GATE_LOGITS", "1") != "0" and buf.C == 32 and tuple(k) == (3, 3, 1)
+                and buf.Z % 8 == 0)
+
+    def _add_gate_logits(self, name, src, k, w, bias):
+        """Last ResidualUnit (conv_only conv + folded shortcut) with the attention gate applied on the fly and the
+        sliding-window blend (vsseg_conv3d_gate_logits).  One launch covers every window of the batch slice."""
+        cout = w.shape[0]
+        wh = pack_conv_weight(w, False).cpu().contiguous()          # HOST fp32 [9][Cin][Cout], passed by value
+        bh = bias.detach().float().cpu().contiguous()
+        att_p = None
+        if self.attention:
+            att = self._att["dec0.att"]
+            av = f32view(att[self._bs[0]:self._bs[0] + self._bs[1]])
+            att_p = C.byref(av)
+            self._keep.append(av)
+        whole = self._bs == (0, self.B)
+        if self.window_levels and whole:
+            outs, n_outs = self._dst_arr, self.B       # one destination view per window
+        else:
+            outs, n_outs = C.byref(self._cur_dst()), 1
+        self._keep += [wh, bh, src]
+        nv = _nvox(src)
+        fl = 2 * nv * 9 * src.C * cout + (2 * nv * src.C if att_p is not None else 0)
+        nb = 4 * (nv * (src.C + (1 if att_p is not None else 0)) + nv * (2 * cout + 1) + 9 * src.C * cout)
+        self.steps.append(_Step(name, self.lib.vsseg_conv3d_gate_logits,
+                                (C.byref(src), att_p, wh.data_ptr(), bh.data_ptr(), cout, outs, n_outs, self.sw_weight),
+                                fl, nb))
+
     def _add_shortcut(self, name, p, src, dst):
         """1x1x1 shortcut conv of a ResidualUnit (convolutions.py:241-250) -> addend buffer."""
         cout = dst.C
@@ -340,9 +373,10 @@ class UNetEvalPlan:
         fl, nb = _conv_cost(src, dst, (1, 1, 1), False, src.C, cout)
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_act8, args, fl, nb))
 
-    def _add_att(self, name, p, buf, hid, k):
+    def _add_att(self, name, p, buf, hid, k, gate=True):
         """AttentionBlock1+2 on act8 buffer `buf` (all channels), in place.  The hidden tensor uses a
-        multiple of 16 channels (zero weights for the padding) so both convs run on tensor cores."""
+        multiple of 16 channels (zero weights for the padding) so both convs run on tensor cores.
+        gate=False: only the map is computed; the consumer applies x*(1+att) on the fly (top level)."""
         cin = buf.C
         src, h = self._v(buf), self._v(hid, 0, _round_up(cin // 2, 16))
         self._add_conv(name + ".conv1", p + "0.conv1.", src, h, k, norm=False, act="relu")
@@ -353,8 +387,8 @@ class UNetEvalPlan:
             self.att_maps.append(att)
         av = f32view(att[self._bs[0]:self._bs[0] + self._bs[1]])
         fused = self._add_smallcout(name + ".conv2", h, av, k, self.sd[p + "0.conv2.conv.weight"],
-                                    self.sd[p + "0.conv2.conv.bias"], 1, 0.0, gate=src)
-        if not fused:
+                                    self.sd[p + "0.conv2.conv.bias"], 1, 0.0, gate=src if gate else None)
+        if gate and not fused:
             self.steps.append(_Step(name + ".gate", self.lib.vsseg_att_gate, (C.byref(src), C.byref(av), C.byref(src)),
                                     2 * _nvox(src) * cin, 4 * _nvox(src) * (2 * cin + 1)))
         self._keep += [src, h, av]
@@ -423,7 +457,7 @@ class UNetEvalPlan:
                 fl, nb = _conv_cost(h, h, k, False, 1, ch[0])
                 self.steps.append(_Step("enc0.unit0" + tag, self.lib.vsseg_conv3d_cin1,
                                         (C.byref(self._cur_src()), C.byref(h), C.byref(g), w.data_ptr(), C.byref(ep)),
-                                        fl, nb - 4 * _nvox(h) * (ch[0] - 1)))
+                                        fl, nb))   # 4 B read + 64 B written per voxel
                 rw = self._dev(self.sd[p + "0.residual.weight"].reshape(-1).float())
                 rbias = self._dev(self.sd[p + "0.residual.bias"].float())
                 self._add_conv("enc0.unit1" + tag, p + "0.conv.unit1.", h, e, k, res_cin1=(rw, rbias))
@@ -440,9 +474,12 @@ class UNetEvalPlan:
                 self._add_conv(f"up{l}" + tag, p + "1.submodule.2.", sub_out, v(cat[l], ch[l], ch[l]), sk, stride=s,
                                transposed=True)
             pr = p + "2."
+            # top level: the gated tensor feeds only the logits conv, so the gate is applied on the fly by
+            # vsseg_conv3d_gate_logits and never written (no dec0.att.gate launch)
+            fuse_top = l == 0 and self._gate_logits_ok(cat[0], k)
             if self.attention:
                 if part != "out":
-                    self._add_att(f"dec{l}.att" + tag, pr + "0.", cat[l], hb[l], k)
+                    self._add_att(f"dec{l}.att" + tag, pr + "0.", cat[l], hb[l], k, gate=not fuse_top)
                 pr = pr + "1."
             if part == "upatt":
                 return
@@ -456,6 +493,9 @@ class UNetEvalPlan:
                     self.out_channels, -1).float()
                 bias = self.sd[pr + "conv.unit0.conv.bias"] + self.sd[pr + "residual.bias"]
                 src = v(cat[0])
+                if fuse_top:
+                    self._add_gate_logits("dec0.gate+logits" + tag, src, k, w, bias)
+                    return
                 # bytes: out read-modify-write + weight map instead of a plain store
                 self._add_smallcout("dec0.logits" + tag, src, self._cur_dst(), k, w, bias, 0, 1.0, self.sw_weight,
                                     nb_extra=4 * _nvox(src) * (self.out_channels + 1))
@@ -487,7 +527,10 @@ class UNetEvalPlan:
             decoder(l)
         if split0:
             decoder(0, "upatt")
-        # ---- fine levels of the decoder, window by window
+        # ---- fine levels of the decoder, window by window (the fused gate+logits launch takes all windows at once)
+        if split0 and self.B <= 16 and self._gate_logits_ok(cat[0], self.kernel_sizes[0]):
+            decoder(0, "out")
+            windows = []
         for bs in windows:
             self._bs = bs
             for l in range(d - 1, -1, -1):
@@ -513,7 +556,7 @@ class UNetEvalPlan:
             self._set(mine, new)
         self.sw_weight.value = sw_weight_ptr
 
-    def run(self, src, dst, sw_weight_ptr: int | None = None, stream=None):
+    def run(self, src, dst, sw_weight_ptr: int | None = None, stream=None, count=True):
         """Launch the whole forward for one patch batch.
 
         src: [B,1,X,Y,Z] fp32 region (may be a strided window of a larger volume);
@@ -527,7 +570,8 @@ class UNetEvalPlan:
             code = st.fn(*st.args, s)
             if code:
                 _lib.check(code, st.name)
-        _lib.count_launch(len(self.steps))
+        if count:
+            _lib.count_launch(len(self.steps))
 
     def profile(self, src, dst, sw_weight_ptr=None, iters=3):
         """Per-step device time (ms, mean of `iters`, CUDA events on the launch stream)."""

@@ -25,7 +25,8 @@ class Act8(C.Structure):
 class F32View(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sc", C.c_int64), ("sx", C.c_int64),
                 ("sy", C.c_int64), ("sz", C.c_int64),
-                ("B", C.c_int32), ("C", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32)]
+                ("B", C.c_int32), ("C", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32),
+                ("reserved", C.c_int32), ("indirect", C.c_void_p)]   # indirect: device cell holding the base address
 
 
 class Epilogue(C.Structure):
@@ -38,6 +39,7 @@ class ConvGeom(C.Structure):
 
 
 _P = C.POINTER
+ABI_VERSION = 2   # VSSEG_ABI_VERSION of include/vsseg_b200.h
 _SIGNATURES = {
     "vsseg_abi_version": (C.c_int, []),
     "vsseg_last_error": (C.c_char_p, []),
@@ -60,6 +62,8 @@ _SIGNATURES = {
     "vsseg_conv3d_cin1": (C.c_int, [_P(F32View), _P(Act8), _P(ConvGeom), C.c_void_p, _P(Epilogue), C.c_void_p]),
     "vsseg_conv3d_smallcout": (C.c_int, [_P(Act8), _P(F32View), _P(ConvGeom), C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_float, C.c_void_p, C.c_void_p]),
+    "vsseg_conv3d_gate_logits": (C.c_int, [_P(Act8), _P(F32View), C.c_void_p, C.c_void_p, C.c_int32, _P(F32View), C.c_int32,
+                                           C.c_void_p, C.c_void_p]),
     "vsseg_att_gate": (C.c_int, [_P(Act8), _P(F32View), _P(Act8), C.c_void_p]),
     "vsseg_maxpool3d": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "vsseg_dice_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
@@ -67,6 +71,10 @@ _SIGNATURES = {
     "vsseg_dice_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsseg_dice_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsseg_dice_general_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsseg_dice_general_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                              C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsseg_bn_stats": (C.c_int, [_P(Act8), C.c_void_p, C.c_void_p]),
     "vsseg_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -89,7 +97,7 @@ _SIGNATURES = {
                                   C.c_float, C.c_float, C.c_int64, C.c_float, C.c_void_p]),
     "vsseg_pack_conv_weight_tc": (C.c_int, [C.c_void_p] + [C.c_int32] * 11 + [C.c_void_p, C.c_void_p]),
     "vsseg_sw_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -120,7 +128,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.vsseg_abi_version() != 1:
+    if lib.vsseg_abi_version() != ABI_VERSION:
         raise NativeLibraryError("libvsseg_b200.so ABI version mismatch")
     _lib = lib
     return lib

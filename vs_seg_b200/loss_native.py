@@ -108,3 +108,93 @@ def dice_spvpa_native(x, att_maps, target, supervised_attention=True, hardness_w
     if not x.is_cuda:
         raise _lib.NativeLibraryError("dice_spvpa_native needs CUDA tensors (no CPU fallback)")
     return _DiceSpvPA.apply(x, target, bool(supervised_attention), bool(hardness_weighting), float(smooth), *att_maps)
+
+
+class _DiceSums(torch.autograd.Function):
+    """sums[b][c] = (sum w t p, sum w t', sum w p') of DiceLoss (reference dice_spvPA.py:133-149) in one native pass,
+    differentiable w.r.t. the prediction (one native elementwise pass backward)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight, act, onehot, squared):
+        lib = _lib.load()
+        B, C = pred.shape[:2]
+        n = pred[0, 0].numel()
+        pc, tc = _f32c(pred), _f32c(target)
+        wc = _f32c(weight) if weight is not None else None
+        sums = torch.zeros((B, 8, 3), dtype=torch.float64, device=pred.device)
+        _lib.check(lib.vsseg_dice_general_sums(pc.data_ptr(), tc.data_ptr(), wc.data_ptr() if wc is not None else None, B, C, n,
+                                               act, int(onehot), int(squared), sums.data_ptr(), _stream(pred.device)),
+                   "dice_general_sums")
+        _lib.count_launch()
+        ctx.save_for_backward(pc, tc, wc if wc is not None else pc.new_empty(0))
+        ctx.meta = (B, C, n, act, int(onehot), int(squared), wc is not None, tuple(pred.shape))
+        return sums[:, :C].float()
+
+    @staticmethod
+    def backward(ctx, gs):
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        lib = _lib.load()
+        pc, tc, wc = ctx.saved_tensors
+        B, C, n, act, onehot, squared, has_w, shape = ctx.meta
+        g8 = torch.zeros((B, 8, 3), dtype=torch.float32, device=pc.device)
+        g8[:, :C] = gs
+        grad = torch.empty(shape, dtype=torch.float32, device=pc.device)
+        _lib.check(lib.vsseg_dice_general_backward(pc.data_ptr(), tc.data_ptr(), wc.data_ptr() if has_w else None, B, C, n, act,
+                                                   onehot, squared, g8.data_ptr(), grad.data_ptr(), _stream(pc.device)),
+                   "dice_general_backward")
+        _lib.count_launch()
+        return grad, None, None, None, None, None
+
+
+def dice_loss_native(mod, input, target, smooth=1e-5):
+    """DiceLoss.forward (reference dice_spvPA.py:90-167) on CUDA tensors: the voxel work is one native reduction
+    (and one native backward pass); include_background / jaccard / reduction act on the B x C sums."""
+    import warnings
+    if not input.is_cuda:
+        raise _lib.NativeLibraryError("dice_loss_native needs CUDA tensors (no CPU fallback)")
+    n_pred_ch = input.shape[1]
+    if n_pred_ch > 8:
+        raise NotImplementedError("native DiceLoss covers up to 8 channels")
+    act = 0
+    if mod.sigmoid:
+        act = 1
+    if mod.softmax:
+        if n_pred_ch == 1:
+            warnings.warn("single channel prediction, `softmax=True` ignored.")
+        else:
+            act = 2
+    if mod.other_act is not None:
+        input = mod.other_act(input)   # the caller's own callable; the reduction below stays native
+    onehot = False
+    if mod.to_onehot_y:
+        if n_pred_ch == 1:
+            warnings.warn("single channel prediction, `to_onehot_y=True` ignored.")
+        else:
+            onehot = True
+    if not mod.include_background and n_pred_ch == 1:
+        warnings.warn("single channel prediction, `include_background=False` ignored.")
+    want = (input.shape[0], 1) + tuple(input.shape[2:]) if onehot else tuple(input.shape)
+    if tuple(target.shape) != want:
+        raise AssertionError(f"ground truth has differing shape ({tuple(target.shape)}) from input ({tuple(input.shape)})")
+    w = mod.hardness_weight
+    if w is not None:
+        if w.requires_grad:
+            raise NotImplementedError("native DiceLoss treats hardness_weight as a constant; the differentiable hardness "
+                                      "weight is the fused Dice_spvPA path")
+        w = w.expand_as(input)
+    sums = _DiceSums.apply(input, target, w, act, onehot, bool(mod.squared_pred))
+    if not mod.include_background and n_pred_ch > 1:
+        sums = sums[:, 1:]
+    inter, ground_o, pred_o = sums.unbind(-1)
+    denom = ground_o + pred_o
+    if mod.jaccard:
+        denom = 2.0 * (denom - inter)
+    f = 1.0 - (2.0 * inter + smooth) / (denom + smooth)
+    if mod.reduction == "mean":
+        return torch.mean(f)
+    if mod.reduction == "sum":
+        return torch.sum(f)
+    if mod.reduction == "none":
+        return f
+    raise ValueError(f'Unsupported reduction: {mod.reduction}, available options are ["mean", "sum", "none"].')

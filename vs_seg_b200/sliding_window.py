@@ -127,6 +127,97 @@ def shard_range(n_items: int, rank: int, world: int):
     return (n_items * rank) // world, (n_items * (rank + 1)) // world
 
 
+class _Program:
+    """The device-side schedule of one sliding-window geometry: zero-fill of the accumulator plus every launch of
+    every window group, captured ONCE in a CUDA graph (the persistent scheduler of the native path).  Windows are
+    read in place through relocatable views (vsseg_f32view.indirect): the graph is re-targeted to a new input
+    volume by storing its address in one 8-byte device cell, so a volume costs the host three calls (cell store,
+    graph launch, finalise) instead of ~250 kernel launches.  The accumulator is owned by the program and reused
+    by every call (it is consumed by ``finalize`` / the reduce right after ``run``).
+
+    Windows run in groups (``VSSEG_SW_GROUP``, default 8): the launches that touch a window's own source /
+    destination run per window, every other layer once per group (see UNetEvalPlan.window_levels)."""
+
+    def __init__(self, model, inputs, roi_size, jobs, imap, image_size):
+        dev = inputs.device
+        self.shape, self.stride = tuple(inputs.shape), tuple(inputs.stride())
+        group = max(1, int(os.environ.get("VSSEG_SW_GROUP", "8")))
+        levels = int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"))
+        # a group plan keeps every activation of its windows resident (~400 B per window voxel): keep it
+        # within a quarter of the free device memory (large roi sizes, e.g. the reference's 384x384x64)
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        per_window = 400 * roi_size[0] * roi_size[1] * roi_size[2]
+        group = max(1, min(group, int(0.25 * free_b // per_window)))
+        self.acc = torch.zeros((inputs.shape[0], model.out_channels) + tuple(image_size), dtype=torch.float32, device=dev)
+        self.cell = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.imap = imap
+        cell = self.cell.data_ptr()
+        self.calls = []   # (plan, srcs, dsts)
+        for g0 in range(0, len(jobs), group):
+            grp = jobs[g0:g0 + group]
+            srcs = [self._src_view(inputs, b, s, roi_size, cell) for b, s in grp]
+            dsts = [f32view(self.acc[b:b + 1], s, roi_size) for b, s in grp]
+            if len(grp) == 1:
+                self.calls.append((model.eval_plan(roi_size, batch=1, device=dev), srcs[0], dsts[0]))
+            else:
+                plan = model.eval_plan(roi_size, batch=len(grp), device=dev, window_levels=levels)
+                self.calls.append((plan, srcs, dsts))
+        self.launches = sum(len(p.steps) for p, _, _ in self.calls)
+        self.graph = None
+        if os.environ.get("VSSEG_SW_GRAPH", "1") != "0" and self.calls:
+            # one eager pass first: lazy module loading, function attributes and the plan caches of the native
+            # library must not happen inside a capture
+            self.cell.fill_(inputs.data_ptr())
+            self._issue()
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._issue()
+
+    @staticmethod
+    def _src_view(inputs, b, start, roi_size, cell):
+        """Relocatable view of one window: byte offset from the volume's base address, which the kernels read
+        from the device cell at run time."""
+        v = f32view(inputs[b:b + 1], start, roi_size)
+        v.ptr = v.ptr - inputs.data_ptr()
+        v.indirect = cell
+        return v
+
+    def _issue(self):
+        self.acc.zero_()
+        wptr = self.imap.data_ptr()
+        for plan, srcs, dsts in self.calls:
+            plan.run(srcs, dsts, wptr, count=False)
+
+    def run(self, inputs):
+        """Accumulate every window of `inputs` (same layout as the volume the program was built for)."""
+        if tuple(inputs.shape) != self.shape or tuple(inputs.stride()) != self.stride:
+            raise ValueError("sliding-window program called with a different volume layout")
+        self.cell.fill_(inputs.data_ptr())   # the value travels as a kernel argument: no host buffer to race on
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._issue()
+        _lib.count_launch(self.launches)
+        return self.acc
+
+
+_PROGRAMS: dict = {}
+
+
+def _program(model, inputs, roi_size, jobs, imap, image_size, extra):
+    """Cached _Program for (model weights, volume layout, geometry, shard)."""
+    key = (id(model), model._weights_version(), tuple(inputs.shape), tuple(inputs.stride()), str(inputs.device),
+           tuple(roi_size), extra, os.environ.get("VSSEG_SW_GROUP", "8"), os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"),
+           os.environ.get("VSSEG_SW_GRAPH", "1"))
+    prog = _PROGRAMS.get(key)
+    if prog is None:
+        if len(_PROGRAMS) >= 3:   # each program owns an accumulator volume and a captured graph
+            _PROGRAMS.clear()
+        prog = _PROGRAMS[key] = _Program(model, inputs, roi_size, jobs, imap, image_size)
+    return prog
+
+
 def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="constant", sigma_scale=0.125,
                               padding_mode="constant", cval=0.0, sw_batch_size=1, window_shard=None):
     """Steps 1-6 of the MONAI algorithm: returns (acc [B,C,*img], cnt [*img], lows, image_size_)."""
@@ -149,30 +240,12 @@ def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="c
         jobs = jobs[lo:hi]
     model = _native_model(predictor)
     if model is not None and inputs.is_cuda and nd == 3:
+        if model.training:
+            raise RuntimeError("the native sliding-window path runs the eval plan: call model.eval() first")
         if inputs.dtype != torch.float32:
             inputs = inputs.float()
-        # windows run in groups: the fine levels of the net window by window (each launch fills the GPU),
-        # the coarse levels once per group (latency-bound launches, see UNetEvalPlan).  Every window still
-        # reads its input in place and blends its logits straight into the accumulator.
-        group = max(1, int(os.environ.get("VSSEG_SW_GROUP", "8")))
-        levels = int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"))
-        # a group plan keeps every activation of its windows resident (~400 B per window voxel): keep it
-        # within a quarter of the free device memory (large roi sizes, e.g. the reference's 384x384x64)
-        free_b, _ = torch.cuda.mem_get_info(inputs.device)
-        per_window = 400 * roi_size[0] * roi_size[1] * roi_size[2]
-        group = max(1, min(group, int(0.25 * free_b // per_window)))
-        acc = torch.zeros((batch, model.out_channels) + image_size, dtype=torch.float32, device=inputs.device)
-        wptr = imap.data_ptr()
-        for g0 in range(0, len(jobs), group):
-            grp = jobs[g0:g0 + group]
-            srcs = [f32view(inputs[b:b + 1], s, roi_size) for b, s in grp]
-            dsts = [f32view(acc[b:b + 1], s, roi_size) for b, s in grp]
-            if len(grp) == 1:
-                model.eval_plan(roi_size, batch=1, device=inputs.device).run(srcs[0], dsts[0], wptr)
-            else:
-                plan = model.eval_plan(roi_size, batch=len(grp), device=inputs.device, window_levels=levels)
-                plan.run(srcs, dsts, wptr)
-        return acc, cnt, lows, image_size_
+        prog = _program(model, inputs, roi_size, jobs, imap, image_size, (overlap, str(mode), sigma_scale, window_shard))
+        return prog.run(inputs), cnt, lows, image_size_
     acc = None
     for g0 in range(0, len(jobs), sw_batch_size):
         grp = jobs[g0:g0 + sw_batch_size]
@@ -190,10 +263,19 @@ def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="c
     return acc, cnt, lows, image_size_
 
 
+def _label_arg(label_b):
+    """(tensor kept alive, pointer, is_u8) of one batch entry's label for vsseg_sw_finalize: uint8 / bool labels
+    are read as bytes (4x less traffic than the reference's float labels), anything else as fp32."""
+    if label_b.dtype in (torch.uint8, torch.bool):
+        t = label_b.contiguous().view(torch.uint8)
+        return t, t.data_ptr(), 1
+    t = label_b.contiguous().float()
+    return t, t.data_ptr(), 0
+
+
 def finalize(acc, cnt, lows, image_size_, label=None, return_mask=False):
     """Step 7: acc / cnt and crop of the padding.  On CUDA this is one native kernel that can also
     emit the argmax mask and the hard-Dice sums of VSparams.compute_dice_score."""
-    nd = acc.dim() - 2
     crop = (slice(None), slice(None)) + tuple(slice(lo, lo + n) for lo, n in zip(lows, image_size_))
     if not acc.is_cuda:
         out = (acc / cnt)[crop]
@@ -208,16 +290,45 @@ def finalize(acc, cnt, lows, image_size_, label=None, return_mask=False):
         raise ValueError("label must have the (un-padded) image shape equal to the accumulator's")
     s = torch.cuda.current_stream(acc.device).cuda_stream
     for b in range(B):
-        lab = label[b].contiguous().float() if label is not None else None
+        keep, lptr, u8 = _label_arg(label[b]) if label is not None else (None, None, 0)
         _lib.check(lib.vsseg_sw_finalize(acc[b].data_ptr(), cnt.data_ptr(), out[b].data_ptr(), Cc, n,
-                                         mask[b].data_ptr() if mask is not None else None,
-                                         lab.data_ptr() if lab is not None else None,
+                                         mask[b].data_ptr() if mask is not None else None, lptr, u8,
                                          sums[b].data_ptr() if sums is not None else None, s), "sw_finalize")
         _lib.count_launch()
     out = out[crop]
     if return_mask or label is not None:
         return out, (mask[crop[:1] + (slice(None),) + crop[2:]] if mask is not None else None), sums
     return out
+
+
+def dice_from_sums(sums, smooth=1e-5):
+    """Hard foreground Dice per batch entry from the sums of vsseg_sw_finalize: (2I + eps) / (G + P + eps), i.e.
+    1 - DiceLoss(include_background=False, to_onehot_y=True) of the one-hot argmax (reference VSparams.py:393-408)."""
+    return (2.0 * sums[:, 0] + smooth) / (sums[:, 1] + sums[:, 2] + smooth)
+
+
+def hard_dice(probabilities: torch.Tensor, label: torch.Tensor, return_mask=False, smooth=1e-5):
+    """VSparams.compute_dice_score on the device in ONE launch: argmax over the class dimension, foreground
+    Dice sums against `label` (and optionally the uint8 argmax mask).  probabilities: [B,C,*spatial] fp32 CUDA,
+    label: [B,1,*spatial] (float / uint8 / bool).  Returns a [B] fp64 device tensor (no host sync)."""
+    if not probabilities.is_cuda:
+        raise _lib.NativeLibraryError("hard_dice runs on CUDA tensors only (no CPU fallback)")
+    lib = _lib.load()
+    p = probabilities.contiguous().float()
+    B, Cc = p.shape[:2]
+    n = p[0, 0].numel()
+    if label.shape[0] != B or label[0].numel() != n:
+        raise ValueError("label must be [B,1,*spatial] with the spatial shape of the probabilities")
+    sums = torch.zeros((B, 3), dtype=torch.float64, device=p.device)
+    mask = torch.empty((B, 1) + tuple(p.shape[2:]), dtype=torch.uint8, device=p.device) if return_mask else None
+    s = torch.cuda.current_stream(p.device).cuda_stream
+    for b in range(B):
+        keep, lptr, u8 = _label_arg(label[b])
+        _lib.check(lib.vsseg_sw_finalize(p[b].data_ptr(), None, None, Cc, n, mask[b].data_ptr() if mask is not None else None,
+                                         lptr, u8, sums[b].data_ptr(), s), "sw_finalize")
+        _lib.count_launch()
+    d = dice_from_sums(sums, smooth)
+    return (d, mask) if return_mask else d
 
 
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable,

@@ -55,8 +55,12 @@ class Act8Buffer:
         return self
 
 
-def f32view(t: torch.Tensor, offset=(0, 0, 0), size=None) -> _lib.F32View:
-    """View of a [B,C,X,Y,Z] fp32 tensor region starting at spatial `offset` with spatial `size`."""
+def f32view(t: torch.Tensor, offset=(0, 0, 0), size=None, cell: int | None = None) -> _lib.F32View:
+    """View of a [B,C,X,Y,Z] fp32 tensor region starting at spatial `offset` with spatial `size`.
+
+    cell: device address of an 8-byte cell that will hold ``t.data_ptr()`` at run time; the view then stores
+    only the region's byte offset (relocatable view, include/vsseg_b200.h) so that launches captured in a
+    CUDA graph follow whatever volume the cell points to."""
     if t.dtype != torch.float32 or t.dim() != 5:
         raise ValueError("f32view needs a 5-D float32 tensor")
     B, Cc = t.shape[0], t.shape[1]
@@ -65,5 +69,7 @@ def f32view(t: torch.Tensor, offset=(0, 0, 0), size=None) -> _lib.F32View:
     X, Y, Z = size if size is not None else (t.shape[2] - ox, t.shape[3] - oy, t.shape[4] - oz)
     if ox < 0 or oy < 0 or oz < 0 or ox + X > t.shape[2] or oy + Y > t.shape[3] or oz + Z > t.shape[4]:
         raise ValueError("f32view region outside the tensor")
-    ptr = t.data_ptr() + 4 * (ox * sx + oy * sy + oz * sz)
-    return _lib.F32View(ptr, sb, sc, sx, sy, sz, B, Cc, X, Y, Z)
+    off = 4 * (ox * sx + oy * sy + oz * sz)
+    if cell is not None:
+        return _lib.F32View(off, sb, sc, sx, sy, sz, B, Cc, X, Y, Z, 0, cell)
+    return _lib.F32View(t.data_ptr() + off, sb, sc, sx, sy, sz, B, Cc, X, Y, Z, 0, None)
