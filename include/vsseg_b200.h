@@ -183,10 +183,13 @@ int vsseg_conv3d_smallcout(const vsseg_act8* in, const vsseg_f32view* out, const
  *   x: act8 [B,Cin,X,Y,Z], Cin % 8 == 0, Cin <= 32;  att: [B,1,X,Y,Z] or NULL (no gate)
  *   w_host: HOST fp32 [9 taps (tx*3+ty)][Cin][Cout]; bias_host: HOST [Cout] (passed to the kernel by value)
  *   outs: n_outs views [*,Cout,X,Y,Z]; n_outs == 1: one view covering all B entries, n_outs == B: entry b -> outs[b]
- *   (the windows of a sliding-window group land at different offsets of the accumulator). */
+ *   (the windows of a sliding-window group land at different offsets of the accumulator).
+ *   atomic_blend: blend with red.global.add.f32.  REQUIRED when the destination regions of one launch overlap
+ *   (several overlapping windows in one launch); the sum order is then unspecified.  With 0 the blend is a plain
+ *   read-modify-write: one window per launch, launches ordered on the stream, i.e. MONAI's accumulation order. */
 int vsseg_conv3d_gate_logits(const vsseg_act8* x, const vsseg_f32view* att, const float* w_host,
                              const float* bias_host, int32_t cout, const vsseg_f32view* outs, int32_t n_outs,
-                             const float* sw_weight, void* stream);
+                             const float* sw_weight, int32_t atomic_blend, void* stream);
 
 /* Attention gate, AttentionBlock2: out = x * (1 + att) (reference attentionblock.py:44-47).
  * att: planar fp32 [B,1,X,Y,Z]; x/out act8 with the same shape (may alias). */

@@ -75,7 +75,7 @@ def test_gate_logits_matches_torch(B, dims, cout, gate, blend, multi):
         ov = f32view(big_d, off, dims)
         outs, n_outs = C.byref(ov), 1
     vlib.check(lib.vsseg_conv3d_gate_logits(C.byref(xv), C.byref(av) if gate else None, wh.data_ptr(), bh.data_ptr(), cout,
-                                            outs, n_outs, sw_d.data_ptr() if blend else None,
+                                            outs, n_outs, sw_d.data_ptr() if blend else None, 1 if multi else 0,
                                             torch.cuda.current_stream().cuda_stream), "gate_logits")
     got = big_d.cpu()
     region = (slice(None), slice(None)) + tuple(slice(o, o + d) for o, d in zip(off, dims))

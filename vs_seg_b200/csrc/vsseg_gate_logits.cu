@@ -30,11 +30,11 @@ struct GateLogitsArgs {
     vsseg_f32view att, out;
     long long out_off[GL_MAXW];   // n_outs > 1: address (or byte offset from the cell when out.indirect) of entry b's view
     const float* sw_weight;
-    int has_att, n_outs;
+    int has_att, n_outs, atomic;
     int TY, ny, L;                // y lines emitted per tile, y tiles, lines staged per tile (TY + 2 halo lines when ny > 1)
     int XT, nxs, nz;              // x rows per segment, x segments, z tiles
     float bias[2];
-    float w[9 * GL_CIN * 2];      // [tap = tx*3+ty][cin][COUT]
+    alignas(16) float w[9 * GL_CIN * 2];      // [tap = tx*3+ty][cin][COUT]
 };
 
 template <int COUT>
@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(GL_MAXL* GL_TZ, 2) gate_logits_kernel(const __
         for (int o = 0; o < COUT; ++o) {
             float* q = outp + o * a.out.sc + xo * a.out.sx;
             const float r = v[o] + a.bias[o];
-            if (swp) *q += sw * r;
-            else *q = r;
+            if (!swp) *q = r;
+            else if (a.atomic) atomicAdd(q, sw * r);   // overlapping windows of one launch (red.global.add.f32)
+            else *q += sw * r;
         }
     };
 
@@ -100,13 +101,29 @@ __global__ void __launch_bounds__(GL_MAXL* GL_TZ, 2) gate_logits_kernel(const __
             for (int cg = 0; cg < NCG; ++cg) {
                 float f[8];
                 unpack8(ldg128(p + cg * cgs), ldg128(p + cg * cgs + lo), f);
+                if constexpr (COUT == 2) {
+                    // packed fp32 FMAs (fma.rn.f32x2, sm_100): both output channels of a tap in one instruction -
+                    // the 576 FMAs per voxel are what bounds this kernel, not its 150 B of traffic
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
+                    for (int c = 0; c < 8; ++c) {
+                        const float2 ff = make_float2(f[c], f[c]);
 #pragma unroll
-                    for (int k = 0; k < 9; ++k)
+                        for (int k = 0; k < 9; ++k) {
+                            const float2 w2 = *reinterpret_cast<const float2*>(&a.w[((k * NCG + cg) * 8 + c) * 2]);
+                            const float2 r = __ffma2_rn(ff, w2, make_float2(P[k][0], P[k][1]));
+                            P[k][0] = r.x;
+                            P[k][1] = r.y;
+                        }
+                    }
+                } else {
 #pragma unroll
-                        for (int o = 0; o < COUT; ++o)
-                            P[k][o] = fmaf(f[c], a.w[((k * NCG + cg) * 8 + c) * COUT + o], P[k][o]);
+                    for (int c = 0; c < 8; ++c)
+#pragma unroll
+                        for (int k = 0; k < 9; ++k)
+#pragma unroll
+                            for (int o = 0; o < COUT; ++o)
+                                P[k][o] = fmaf(f[c], a.w[((k * NCG + cg) * 8 + c) * COUT + o], P[k][o]);
+                }
             }
             if (attp) {
                 const float g = 1.0f + __ldg(attp + xi * a.att.sx);
@@ -153,7 +170,7 @@ using namespace vsseg;
 
 extern "C" int vsseg_conv3d_gate_logits(const vsseg_act8* x, const vsseg_f32view* att, const float* w_host,
                                         const float* bias_host, int32_t cout, const vsseg_f32view* outs, int32_t n_outs,
-                                        const float* sw_weight, void* stream) {
+                                        const float* sw_weight, int32_t atomic_blend, void* stream) {
     VSSEG_REQUIRE(x && x->hi && x->C == GL_CIN && x->B >= 1 && x->X >= 1 && x->Y >= 1 && x->Z >= GL_TZ && x->Z % GL_TZ == 0,
                   "conv3d_gate_logits: x must be act8 with %d channels and Z %% %d == 0", GL_CIN, GL_TZ);
     VSSEG_REQUIRE(w_host && bias_host && (cout == 1 || cout == 2), "conv3d_gate_logits: Cout must be 1 or 2");
@@ -175,6 +192,7 @@ extern "C" int vsseg_conv3d_gate_logits(const vsseg_act8* x, const vsseg_f32view
         a.out_off[i] = (long long)(intptr_t)o.ptr;
     }
     a.sw_weight = sw_weight;
+    a.atomic = atomic_blend ? 1 : 0;
     const int Y = x->Y, X = x->X;
     a.ny = Y <= GL_MAXL ? 1 : (Y + 63) / 64;
     a.TY = (Y + a.ny - 1) / a.ny;

@@ -347,8 +347,11 @@ class UNetEvalPlan:
             att_p = C.byref(av)
             self._keep.append(av)
         whole = self._bs == (0, self.B)
+        atomic = 0
         if self.window_levels and whole:
-            outs, n_outs = self._dst_arr, self.B       # one destination view per window
+            # every window of the group in ONE launch: their destination regions overlap, so the blend must be
+            # atomic (sum order unspecified).  Opt-in: the default keeps one launch per window = MONAI's order
+            outs, n_outs, atomic = self._dst_arr, self.B, 1
         else:
             outs, n_outs = C.byref(self._cur_dst()), 1
         self._keep += [wh, bh, src]
@@ -356,7 +359,7 @@ class UNetEvalPlan:
         fl = 2 * nv * 9 * src.C * cout + (2 * nv * src.C if att_p is not None else 0)
         nb = 4 * (nv * (src.C + (1 if att_p is not None else 0)) + nv * (2 * cout + 1) + 9 * src.C * cout)
         self.steps.append(_Step(name, self.lib.vsseg_conv3d_gate_logits,
-                                (C.byref(src), att_p, wh.data_ptr(), bh.data_ptr(), cout, outs, n_outs, self.sw_weight),
+                                (C.byref(src), att_p, wh.data_ptr(), bh.data_ptr(), cout, outs, n_outs, self.sw_weight, atomic),
                                 fl, nb))
 
     def _add_shortcut(self, name, p, src, dst):
@@ -527,8 +530,10 @@ class UNetEvalPlan:
             decoder(l)
         if split0:
             decoder(0, "upatt")
-        # ---- fine levels of the decoder, window by window (the fused gate+logits launch takes all windows at once)
-        if split0 and self.B <= 16 and self._gate_logits_ok(cat[0], self.kernel_sizes[0]):
+        # ---- fine levels of the decoder, window by window (VSSEG_SW_ATOMIC=1: the fused gate+logits launch takes all
+        # windows at once and blends with atomics)
+        if (split0 and self.B <= 16 and self._gate_logits_ok(cat[0], self.kernel_sizes[0])
+                and os.environ.get("VSSEG_SW_ATOMIC", "0") == "1"):
             decoder(0, "out")
             windows = []
         for bs in windows:

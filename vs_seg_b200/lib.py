@@ -63,7 +63,7 @@ _SIGNATURES = {
     "vsseg_conv3d_smallcout": (C.c_int, [_P(Act8), _P(F32View), _P(ConvGeom), C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_float, C.c_void_p, C.c_void_p]),
     "vsseg_conv3d_gate_logits": (C.c_int, [_P(Act8), _P(F32View), C.c_void_p, C.c_void_p, C.c_int32, _P(F32View), C.c_int32,
-                                           C.c_void_p, C.c_void_p]),
+                                           C.c_void_p, C.c_int32, C.c_void_p]),
     "vsseg_att_gate": (C.c_int, [_P(Act8), _P(F32View), _P(Act8), C.c_void_p]),
     "vsseg_maxpool3d": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "vsseg_dice_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
