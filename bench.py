@@ -6,8 +6,8 @@
 A step = the sliding-window inference of ONE synthetic volume (BASELINE.json configs[3]:
 384x384x160, 128^3 window, overlap 0.25, gaussian blending -> 32 patches) including the finalise
 kernel (probabilities, argmax mask, Dice sums).  N>1 (torchrun): the 32 windows of every volume are
-sharded by patch index over the ranks and the un-normalised accumulator is reduced to rank 0 with
-one NCCL reduce (strong scaling of a fixed volume).  One JSON line is printed by rank 0.
+sharded by patch index over the ranks, which blend them straight into rank 0's accumulator over NVLink
+peer memory (strong scaling of a fixed volume).  One JSON line is printed by rank 0.
 
 --impl reference times the CPU oracle (restatement of the reference's torch/MONAI path; the
 reference itself cannot be imported on the GPU box) on the host cores, one patch per step.
@@ -112,7 +112,8 @@ def bench_config(world):
             "patches_per_step": 32, "weights": "seeded random init",
             "l2_policy": f"GPU arm: {N_ROT} rotating volumes (283 MB each) > 126 MB L2",
             "gpu_schedule": f"window groups of {group}, one captured CUDA graph per volume; "
-                            + (f"patch-index shard x{world}, 1 NCCL reduce/volume" if world > 1 else "1 GPU")}
+                            + (f"patch-index shard x{world}, blended into rank 0's accumulator over NVLink peer memory"
+                               if world > 1 else "1 GPU")}
 
 
 def run_reference(args):
@@ -180,14 +181,15 @@ def main():
     predictor.native_model = net
 
     host = [synth_volume(i) for i in range(N_ROT)]
-    pinned = [(v.pin_memory(), l.pin_memory()) for v, l in host]
-    vols = [(v.to(dev), l.to(dev)) for v, l in host]
+    # the label travels as uint8 (1 byte per voxel; the finalise kernel reads it as bytes)
+    pinned = [(v.pin_memory(), l.to(torch.uint8).pin_memory()) for v, l in host]
+    vols = [(v.to(dev), l.to(torch.uint8).to(dev)) for v, l in host]
     n_win = len(sw.window_starts(VOLUME, ROI, 0.25))
     mask_host = torch.empty((1, 1) + VOLUME, dtype=torch.uint8).pin_memory()
     sums_host = torch.empty((1, 3), dtype=torch.float64).pin_memory()
 
     def infer(vol, label):
-        # windows sharded by index over the ranks, one NCCL reduce of the accumulator to rank 0
+        # windows sharded by index over the ranks, blended into rank 0's accumulator over peer memory
         return par.sharded_sliding_window_inference(vol, ROI, 1, predictor, 0.25, "gaussian", label=label,
                                                     return_mask=True)
 
@@ -201,12 +203,13 @@ def main():
     # a rank only needs the x slab its windows cover (windows are sharded in x-slowest order); the label is
     # only read by rank 0's finalise kernel
     slab = par.shard_slab(VOLUME, ROI, 0.25, rank, world) or (0, 0)
-    h2d_bytes = (slab[1] - slab[0]) * VOLUME[1] * VOLUME[2] * 4 + (host[0][1].numel() * 4 if rank == 0 else 0)
+    h2d_bytes = (slab[1] - slab[0]) * VOLUME[1] * VOLUME[2] * 4 + (host[0][1].numel() if rank == 0 else 0)
 
     # end-to-end step: the volume comes from pinned host memory and the mask + Dice sums go back to the host
     # every step.  The copy of step i+1's input is issued on a copy stream while step i computes (two device
     # buffers); every step still pays one host->device and one device->host copy inside the timed region.
     copy_stream = torch.cuda.Stream(dev)
+    d2h_stream = torch.cuda.Stream(dev)   # results leave on their own stream: the next volume's kernels do not wait
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
     state = {"prefetched": None}
@@ -232,10 +235,16 @@ def main():
         free[i % 2].record(cur)
         if res is not None:
             _, mask, sums = res
-            mask_host.copy_(mask, non_blocking=True)
-            sums_host.copy_(sums, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                mask_host.copy_(mask, non_blocking=True)
+                sums_host.copy_(sums, non_blocking=True)
+            mask.record_stream(d2h_stream)
+            sums.record_stream(d2h_stream)
 
-    def timed(fn, warmup, steps):
+    def timed(fn, warmup, steps, finish=None):
         for i in range(warmup):
             fn(i)
         torch.cuda.synchronize(dev)
@@ -247,6 +256,8 @@ def main():
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if finish is not None:
+            finish()   # the timed region ends when the last result has reached the host
         e1.record()
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -262,7 +273,7 @@ def main():
         if rank == 0:
             clocks.start()
         ms, launches = timed(step_resident, max(args.warmup, 3), args.steps)
-        ms_e2e, _ = timed(step_e2e, 2, args.steps)
+        ms_e2e, _ = timed(step_e2e, 2, args.steps, finish=lambda: torch.cuda.current_stream(dev).wait_stream(d2h_stream))
         clk = clocks.stop() if rank == 0 else None
 
         # parity leg, part 1 (all ranks): the SAME call the timed region makes, on synthetic volume 0 - window
@@ -272,6 +283,8 @@ def main():
             res = infer(vols[0][0], vols[0][1])
             if res is not None:
                 par_res = (res[0].cpu(), res[1].cpu(), res[2].cpu())
+            if world > 1 and par._PEER:
+                next(iter(par._PEER.values())).check()   # no rank timed out in the peer hand-shake
             torch.cuda.synchronize(dev)
 
         if rank != 0:
@@ -371,7 +384,7 @@ def main():
             diff_mask = mask.long() != ref_mask
             dice_native = ((2 * sums[0, 0] + 1e-5) / (sums[0, 1] + sums[0, 2] + 1e-5)).item()
             parity = {"scope": "full finalised volume of the timed call (window groups of 8, captured graph, blend in the "
-                               "last kernel" + (f", NCCL reduce over {world} ranks" if world > 1 else "") + ") vs sw_oracle",
+                               "last kernel" + (f", peer-memory blend of {world} ranks" if world > 1 else "") + ") vs sw_oracle",
                       "max_abs_err_logits": (got - ref).abs().max().item(),
                       "argmax_flips_margin_gt_1e-4": ((got.argmax(1) != ref.argmax(1)) & (margin > 1e-4)).sum().item(),
                       "mask_kernel_flips_margin_gt_1e-4": (diff_mask[:, 0] & (margin > 1e-4)).sum().item(),

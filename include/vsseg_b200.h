@@ -204,6 +204,24 @@ int vsseg_att_gate(const vsseg_act8* x, const vsseg_f32view* att, const vsseg_ac
 int vsseg_sw_finalize(const float* acc, const float* cnt, float* out, int32_t C, int64_t n,
                       uint8_t* mask, const void* label, int32_t label_u8, double* sums, void* stream);
 
+/* ---- multi-GPU sliding window over peer memory (one node, one process per GPU) -----------------
+ * The reference has no multi-GPU path; windows are independent (VSparams.py:556-574: eval mode, sw_batch_size 1), so
+ * rank r runs a contiguous block of the window list and blends it with atomic adds (vsseg_conv3d_gate_logits,
+ * atomic_blend = 1) into the accumulator of the destination rank, mapped into every process with CUDA IPC.
+ *   vsseg_peer_alloc   cudaMalloc + zero fill + IPC handle (64 bytes, HOST buffer) of an allocation peers may map
+ *   vsseg_peer_open    maps a peer's allocation into this process (peer access enabled lazily); *ptr_host = device pointer
+ *   vsseg_peer_close / vsseg_peer_free   unmap / release
+ *   vsseg_flag_set     one-thread kernel: system-scope fence, then *flag = value (flag may live in peer memory): "all my
+ *                      blends of volume k are done" / "buffer released"
+ *   vsseg_flag_wait    one-thread kernel: spins until every flags[0..n) >= target (acquire, system scope); gives up after
+ *                      timeout_cycles SM clocks and sets *err (DEVICE int, may be NULL) instead of hanging the GPU */
+int vsseg_peer_alloc(int64_t bytes, void** ptr_host, void* handle64_host);
+int vsseg_peer_open(const void* handle64_host, void** ptr_host);
+int vsseg_peer_close(void* ptr);
+int vsseg_peer_free(void* ptr);
+int vsseg_flag_set(int64_t* flag, int64_t value, void* stream);
+int vsseg_flag_wait(const int64_t* flags, int32_t n, int64_t target, int64_t timeout_cycles, int32_t* err, void* stream);
+
 /* ---- Dice_spvPA loss (reference params/losses/dice_spvPA.py:90-167, :238-297) -----------------------
  * All tensors planar fp32, contiguous.  The loss is assembled from "terms": the 2-class logits term
  * (softmax + one-hot + hardness weight w = lambda*|p - t| + 1 - lambda, gradient flowing through w) and

@@ -200,6 +200,8 @@ class UNetEvalPlan:
         self.src, self.dst = self.srcs[0], self.dsts[0]
         self._bs = (0, self.B)   # batch slice the step being emitted works on
         self.sw_weight = C.c_void_p(None)
+        self.atomic_blend = C.c_int32(0)   # set per run(): blend with atomics (several writers of one accumulator)
+        self._has_plain_blend = False      # a blending launch that cannot use atomics is part of the plan
         self._build()
 
     # -- helpers ------------------------------------------------------------------------
@@ -347,7 +349,7 @@ class UNetEvalPlan:
             att_p = C.byref(av)
             self._keep.append(av)
         whole = self._bs == (0, self.B)
-        atomic = 0
+        atomic = self.atomic_blend
         if self.window_levels and whole:
             # every window of the group in ONE launch: their destination regions overlap, so the blend must be
             # atomic (sum order unspecified).  Opt-in: the default keeps one launch per window = MONAI's order
@@ -500,6 +502,7 @@ class UNetEvalPlan:
                     self._add_gate_logits("dec0.gate+logits" + tag, src, k, w, bias)
                     return
                 # bytes: out read-modify-write + weight map instead of a plain store
+                self._has_plain_blend = True
                 self._add_smallcout("dec0.logits" + tag, src, self._cur_dst(), k, w, bias, 0, 1.0, self.sw_weight,
                                     nb_extra=4 * _nvox(src) * (self.out_channels + 1))
 
@@ -547,7 +550,7 @@ class UNetEvalPlan:
     def _set(self, view, new):
         C.memmove(C.byref(view), C.byref(new), C.sizeof(_lib.F32View))
 
-    def _bind(self, src, dst, sw_weight_ptr):
+    def _bind(self, src, dst, sw_weight_ptr, atomic=False):
         srcs = list(src) if isinstance(src, (list, tuple)) else [src]
         dsts = list(dst) if isinstance(dst, (list, tuple)) else [dst]
         nb = 1 if self.window_levels else self.B
@@ -560,16 +563,20 @@ class UNetEvalPlan:
         for mine, new in zip(self.srcs + self.dsts, srcs + dsts):
             self._set(mine, new)
         self.sw_weight.value = sw_weight_ptr
+        if atomic and self._has_plain_blend:
+            raise _lib.NativeLibraryError("this plan blends with a launch that has no atomic mode")
+        self.atomic_blend.value = 1 if atomic else 0
 
-    def run(self, src, dst, sw_weight_ptr: int | None = None, stream=None, count=True):
+    def run(self, src, dst, sw_weight_ptr: int | None = None, stream=None, count=True, atomic=False):
         """Launch the whole forward for one patch batch.
 
         src: [B,1,X,Y,Z] fp32 region (may be a strided window of a larger volume);
         dst: [B,out_channels,X,Y,Z] fp32 region; if ``sw_weight_ptr`` is given the logits are
         blended (dst += weight * logits) instead of stored.  A plan built with ``window_levels`` takes
-        lists of B single-window views instead.
+        lists of B single-window views instead.  ``atomic``: blend with red.global.add (several ranks write one
+        accumulator over peer memory).
         """
-        self._bind(src, dst, sw_weight_ptr)
+        self._bind(src, dst, sw_weight_ptr, atomic)
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         for st in self.steps:
             code = st.fn(*st.args, s)

@@ -65,6 +65,12 @@ _SIGNATURES = {
     "vsseg_conv3d_gate_logits": (C.c_int, [_P(Act8), _P(F32View), C.c_void_p, C.c_void_p, C.c_int32, _P(F32View), C.c_int32,
                                            C.c_void_p, C.c_int32, C.c_void_p]),
     "vsseg_att_gate": (C.c_int, [_P(Act8), _P(F32View), _P(Act8), C.c_void_p]),
+    "vsseg_peer_alloc": (C.c_int, [C.c_int64, _P(C.c_void_p), C.c_void_p]),
+    "vsseg_peer_open": (C.c_int, [C.c_void_p, _P(C.c_void_p)]),
+    "vsseg_peer_close": (C.c_int, [C.c_void_p]),
+    "vsseg_peer_free": (C.c_int, [C.c_void_p]),
+    "vsseg_flag_set": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "vsseg_flag_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "vsseg_maxpool3d": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p]),
     "vsseg_dice_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_void_p,
                                   C.c_void_p]),

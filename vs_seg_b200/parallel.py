@@ -1,12 +1,20 @@
-"""Multi-GPU sliding-window inference: windows sharded by index, one reduce of the accumulator.
+"""Multi-GPU sliding-window inference: windows sharded by index over the ranks of one node.
 
 Windows are independent in eval mode, so rank r runs the contiguous block
-``shard_range(n_windows, r, world)`` of the MONAI window list into its own zero-initialised fp32
-accumulator, and ONE ``reduce(SUM)`` (NCCL over NVLink on GPUs, gloo in the CPU tests) brings the
-un-normalised accumulators to rank 0, which divides by the input-independent weight-sum map
-(``sliding_window.finalize``).  No other collective touches the data path.
+``shard_range(n_windows, r, world)`` of the MONAI window list.  Two ways to assemble the volume on rank ``dst``:
+
+  * peer blend (default on GPUs, vs_seg_b200.peer): the last kernel of the network blends every window with atomic adds
+    straight into ``dst``'s accumulator over NVLink peer memory - the exchange is fused into the compute, there is no
+    reduce pass, no per-rank accumulator and no per-rank zero fill; a two-deep arrive/release hand-shake lets the ranks
+    run one volume ahead of ``dst``'s finalise;
+  * reduce (gloo / CPU tests, foreign predictors, ``VSSEG_SW_PEER=0``): private zero-initialised accumulators and ONE
+    ``reduce(SUM)`` of the un-normalised accumulator to ``dst``.
+
+``dst`` divides by the input-independent weight-sum map (``sliding_window.finalize``).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -14,19 +22,64 @@ import torch.distributed as dist
 from . import sliding_window as sw
 
 
+_PEER: dict = {}
+
+
+def _peer_accumulator(shape, device, group, dst):
+    """The cached PeerAccumulator for one accumulator shape (collective: every rank creates it at the same call)."""
+    from .peer import PeerAccumulator
+    key = (tuple(shape), str(device), id(group), dst)
+    acc = _PEER.get(key)
+    if acc is None:
+        for old in _PEER.values():
+            old.close()
+        _PEER.clear()
+        acc = _PEER[key] = PeerAccumulator(shape, device, group, dst)
+    return acc
+
+
+def _use_peer(inputs, predictor):
+    return (os.environ.get("VSSEG_SW_PEER", "1") != "0" and inputs.is_cuda and inputs.dim() == 5
+            and sw._native_model(predictor) is not None and dist.get_backend() == "nccl")
+
+
 def sharded_sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap=0.25, mode="constant",
                                      sigma_scale=0.125, padding_mode="constant", cval=0.0, group=None, dst=0,
                                      label=None, return_mask=False):
     """Same result as ``sliding_window_inference`` on rank ``dst`` (None on the other ranks).
 
-    Every rank passes the same ``inputs`` (the whole volume).  With ``label`` / ``return_mask`` the
-    result is ``(probabilities, argmax mask, hard-Dice sums)`` as ``sliding_window.finalize`` returns.
+    Every rank passes the same ``inputs`` (the whole volume, or at least the x slab of its windows, see
+    ``shard_slab``).  With ``label`` / ``return_mask`` the result is ``(probabilities, argmax mask, hard-Dice sums)``
+    as ``sliding_window.finalize`` returns.
+
+    On one node with the native CUDA path the ranks blend their windows straight into rank ``dst``'s accumulator over
+    NVLink peer memory (vs_seg_b200.peer; atomic adds, so the sum order of overlapping windows is unspecified - the
+    result agrees with the single-GPU one to fp32 rounding).  ``VSSEG_SW_PEER=0``, CPU tensors and foreign predictors
+    use private accumulators and ONE reduce(SUM) of the un-normalised accumulator to ``dst`` instead.
     """
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         acc, cnt, lows, img = sw.sliding_window_accumulate(inputs, roi_size, predictor, overlap, mode, sigma_scale,
                                                            padding_mode, cval, sw_batch_size)
         return sw.finalize(acc, cnt, lows, img, label=label, return_mask=return_mask)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if _use_peer(inputs, predictor):
+        box = {}
+
+        def peer_acc(shape):
+            box["acc"] = _peer_accumulator(shape, inputs.device, group, dst)
+            return box["acc"].begin()
+
+        _, cnt, lows, img = sw.sliding_window_accumulate(inputs, roi_size, predictor, overlap, mode, sigma_scale,
+                                                         padding_mode, cval, sw_batch_size, window_shard=(rank, world),
+                                                         peer_acc=peer_acc)
+        pa = box["acc"]
+        pa.arrive()
+        res = None
+        if rank == dst:
+            res = sw.finalize(pa.gather(), cnt, lows, img, label=label, return_mask=return_mask)
+            pa.release()
+        pa.end()
+        return res
     acc, cnt, lows, img = sw.sliding_window_accumulate(inputs, roi_size, predictor, overlap, mode, sigma_scale,
                                                        padding_mode, cval, sw_batch_size, window_shard=(rank, world))
     dist.reduce(acc, dst=dst, op=dist.ReduceOp.SUM, group=group)

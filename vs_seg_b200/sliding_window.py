@@ -138,8 +138,9 @@ class _Program:
     Windows run in groups (``VSSEG_SW_GROUP``, default 8): the launches that touch a window's own source /
     destination run per window, every other layer once per group (see UNetEvalPlan.window_levels)."""
 
-    def __init__(self, model, inputs, roi_size, jobs, imap, image_size):
+    def __init__(self, model, inputs, roi_size, jobs, imap, image_size, peer=False):
         dev = inputs.device
+        self.peer = bool(peer)
         self.shape, self.stride = tuple(inputs.shape), tuple(inputs.stride())
         group = max(1, int(os.environ.get("VSSEG_SW_GROUP", "8")))
         levels = int(os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"))
@@ -148,15 +149,21 @@ class _Program:
         free_b, _ = torch.cuda.mem_get_info(dev)
         per_window = 400 * roi_size[0] * roi_size[1] * roi_size[2]
         group = max(1, min(group, int(0.25 * free_b // per_window)))
-        self.acc = torch.zeros((inputs.shape[0], model.out_channels) + tuple(image_size), dtype=torch.float32, device=dev)
-        self.cell = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.acc_shape = (inputs.shape[0], model.out_channels) + tuple(image_size)
+        # peer mode (multi-GPU): the accumulator belongs to the destination rank (vs_seg_b200.peer); its address
+        # comes through a second cell and the blend is atomic.  Otherwise the program owns the accumulator.
+        self.acc = None if self.peer else torch.zeros(self.acc_shape, dtype=torch.float32, device=dev)
+        self.cell = torch.zeros(2, dtype=torch.int64, device=dev)   # [input base, accumulator base]
         self.imap = imap
         cell = self.cell.data_ptr()
         self.calls = []   # (plan, srcs, dsts)
         for g0 in range(0, len(jobs), group):
             grp = jobs[g0:g0 + group]
             srcs = [self._src_view(inputs, b, s, roi_size, cell) for b, s in grp]
-            dsts = [f32view(self.acc[b:b + 1], s, roi_size) for b, s in grp]
+            if self.peer:
+                dsts = [self._acc_view(self.acc_shape, b, s, roi_size, cell + 8) for b, s in grp]
+            else:
+                dsts = [f32view(self.acc[b:b + 1], s, roi_size) for b, s in grp]
             if len(grp) == 1:
                 self.calls.append((model.eval_plan(roi_size, batch=1, device=dev), srcs[0], dsts[0]))
             else:
@@ -167,7 +174,10 @@ class _Program:
         if os.environ.get("VSSEG_SW_GRAPH", "1") != "0" and self.calls:
             # one eager pass first: lazy module loading, function attributes and the plan caches of the native
             # library must not happen inside a capture
-            self.cell.fill_(inputs.data_ptr())
+            self.cell[0].fill_(inputs.data_ptr())
+            if self.peer:   # the warm-up pass blends into a scratch volume
+                scratch = torch.zeros(self.acc_shape, dtype=torch.float32, device=dev)
+                self.cell[1].fill_(scratch.data_ptr())
             self._issue()
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
@@ -183,17 +193,29 @@ class _Program:
         v.indirect = cell
         return v
 
+    @staticmethod
+    def _acc_view(shape, b, start, roi_size, cell):
+        """Relocatable view of one window of a contiguous [B,C,X,Y,Z] accumulator that lives wherever the cell says."""
+        _, Cc, X, Y, Z = shape
+        sz, sy, sx, sc = 1, Z, Y * Z, X * Y * Z
+        off = 4 * (b * Cc * sc + start[0] * sx + start[1] * sy + start[2] * sz)
+        return _lib.F32View(off, Cc * sc, sc, sx, sy, sz, 1, Cc, roi_size[0], roi_size[1], roi_size[2], 0, cell)
+
     def _issue(self):
-        self.acc.zero_()
+        if not self.peer:
+            self.acc.zero_()
         wptr = self.imap.data_ptr()
         for plan, srcs, dsts in self.calls:
-            plan.run(srcs, dsts, wptr, count=False)
+            plan.run(srcs, dsts, wptr, count=False, atomic=self.peer)
 
-    def run(self, inputs):
-        """Accumulate every window of `inputs` (same layout as the volume the program was built for)."""
+    def run(self, inputs, acc_ptr=None):
+        """Accumulate every window of `inputs` (same layout as the volume the program was built for).
+        Peer mode: blend (atomically) into the accumulator at device address `acc_ptr`."""
         if tuple(inputs.shape) != self.shape or tuple(inputs.stride()) != self.stride:
             raise ValueError("sliding-window program called with a different volume layout")
-        self.cell.fill_(inputs.data_ptr())   # the value travels as a kernel argument: no host buffer to race on
+        self.cell[0].fill_(inputs.data_ptr())   # the value travels as a kernel argument: no host buffer to race on
+        if self.peer:
+            self.cell[1].fill_(acc_ptr)
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -205,22 +227,24 @@ class _Program:
 _PROGRAMS: dict = {}
 
 
-def _program(model, inputs, roi_size, jobs, imap, image_size, extra):
+def _program(model, inputs, roi_size, jobs, imap, image_size, extra, peer=False):
     """Cached _Program for (model weights, volume layout, geometry, shard)."""
     key = (id(model), model._weights_version(), tuple(inputs.shape), tuple(inputs.stride()), str(inputs.device),
            tuple(roi_size), extra, os.environ.get("VSSEG_SW_GROUP", "8"), os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"),
-           os.environ.get("VSSEG_SW_GRAPH", "1"))
+           os.environ.get("VSSEG_SW_GRAPH", "1"), bool(peer))
     prog = _PROGRAMS.get(key)
     if prog is None:
         if len(_PROGRAMS) >= 3:   # each program owns an accumulator volume and a captured graph
             _PROGRAMS.clear()
-        prog = _PROGRAMS[key] = _Program(model, inputs, roi_size, jobs, imap, image_size)
+        prog = _PROGRAMS[key] = _Program(model, inputs, roi_size, jobs, imap, image_size, peer)
     return prog
 
 
 def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="constant", sigma_scale=0.125,
-                              padding_mode="constant", cval=0.0, sw_batch_size=1, window_shard=None):
-    """Steps 1-6 of the MONAI algorithm: returns (acc [B,C,*img], cnt [*img], lows, image_size_)."""
+                              padding_mode="constant", cval=0.0, sw_batch_size=1, window_shard=None, peer_acc=None):
+    """Steps 1-6 of the MONAI algorithm: returns (acc [B,C,*img], cnt [*img], lows, image_size_).
+    peer_acc: callable(shape) -> device address of a shared accumulator (vs_seg_b200.peer): the windows of this
+    rank's shard are blended into it with atomics and `acc` is returned as None."""
     nd = inputs.dim() - 2
     if not 0 <= overlap < 1:
         raise AssertionError("overlap must be >= 0 and < 1.")
@@ -244,8 +268,15 @@ def sliding_window_accumulate(inputs, roi_size, predictor, overlap=0.25, mode="c
             raise RuntimeError("the native sliding-window path runs the eval plan: call model.eval() first")
         if inputs.dtype != torch.float32:
             inputs = inputs.float()
-        prog = _program(model, inputs, roi_size, jobs, imap, image_size, (overlap, str(mode), sigma_scale, window_shard))
+        extra = (overlap, str(mode), sigma_scale, window_shard)
+        if peer_acc is not None:
+            prog = _program(model, inputs, roi_size, jobs, imap, image_size, extra, peer=True)
+            prog.run(inputs, peer_acc((inputs.shape[0], model.out_channels) + image_size))
+            return None, cnt, lows, image_size_
+        prog = _program(model, inputs, roi_size, jobs, imap, image_size, extra)
         return prog.run(inputs), cnt, lows, image_size_
+    if peer_acc is not None:
+        raise _lib.NativeLibraryError("the peer-memory accumulator needs the native CUDA path")
     acc = None
     for g0 in range(0, len(jobs), sw_batch_size):
         grp = jobs[g0:g0 + sw_batch_size]
