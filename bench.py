@@ -116,6 +116,65 @@ def bench_config(world):
                                if world > 1 else "1 GPU")}
 
 
+def train_record(dev, world, steps=5):
+    """Secondary record (BASELINE configs[2], and configs[4] under torchrun): one training step = native train-mode
+    forward + Dice_spvPA + native backward (+ ONE all-reduce of the flat gradient at N > 1) + fused Adam on a
+    synthetic batch of 2 x 128^3 per GPU.  CUDA events, max over ranks."""
+    import torch.distributed as dist
+    from oracle.unet_oracle import CHANNELS, KERNEL_SIZES, SAMPLE_KERNEL_SIZES, STRIDES
+    from params.losses.dice_spvPA import Dice_spvPA
+    from params.networks.nets.unet2d5_spvPA import UNet2d5_spvPA
+    from vs_seg_b200 import ddp
+    from vs_seg_b200 import lib as vlib
+    from vs_seg_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    net = UNet2d5_spvPA(dimensions=3, in_channels=1, out_channels=2, channels=CHANNELS, strides=STRIDES,
+                        kernel_sizes=KERNEL_SIZES, sample_kernel_sizes=SAMPLE_KERNEL_SIZES, num_res_units=2,
+                        norm="BATCH", dropout=0.1).to(dev).train()
+    ddp.broadcast_module_state(net)
+    opt = FusedAdam(net.parameters(), lr=1e-4, weight_decay=1e-7)
+    red = ddp.GradReducer(net, opt)
+    crit = Dice_spvPA(to_onehot_y=True, softmax=True)
+    g = torch.Generator().manual_seed(2000 + (dist.get_rank() if world > 1 else 0))
+    x = torch.randn((2, 1) + ROI, generator=g).to(dev)
+    y = (torch.rand((2, 1) + ROI, generator=g) > 0.95).float().to(dev)
+
+    def step():
+        opt.zero_grad()
+        loss = crit(net(x), y)
+        loss.backward()
+        red.reduce()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    l0 = vlib.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps   # host time to ISSUE a step (no sync inside)
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rec = {"workload": "training step, batch 2 x 128^3 per GPU: native fwd + Dice_spvPA + native bwd"
+                       + (f" + 1 NCCL all-reduce of the flat gradient over {world} ranks" if world > 1 else "")
+                       + " + fused Adam (BASELINE configs[2]" + ("/[4])" if world > 1 else ")"),
+           "n_gpus": world, "batch_per_gpu": 2, "ms_per_step": ms.item(), "samples_per_s": 2 * world / (ms.item() * 1e-3),
+           "host_issue_ms_per_step": host_ms, "native_launches_per_step": (vlib.launches() - l0) // steps,
+           "loss": float(loss), "dropout": 0.1, "steps": steps}
+    del net, opt, red
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -157,6 +216,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step record")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -287,6 +347,14 @@ def main():
                 next(iter(par._PEER.values())).check()   # no rank timed out in the peer hand-shake
             torch.cuda.synchronize(dev)
 
+    train = None
+    if not args.no_train:
+        try:
+            train = train_record(dev, world)
+        except Exception as e:  # noqa: BLE001  (secondary record: never lose the headline line)
+            train = {"error": repr(e)[:300]}
+
+    with torch.no_grad():
         if rank != 0:
             dist.destroy_process_group()
             return
@@ -404,7 +472,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
-            "patch_ms_profiled": patch_ms,
+            "patch_ms_profiled": patch_ms, "train": train,
             "notes": "value/e2e: CUDA events around K volumes, max over ranks; e2e copies the rank's x slab of the "
                      "volume (and the label on rank 0) from pinned host memory and the mask + Dice sums back every step; "
                      "h2d_bytes_per_step is rank 0's",

@@ -282,12 +282,14 @@ int vsseg_bn_stats(const vsseg_act8* x, double* sums, void* stream);
 int vsseg_bn_finalize(const double* sums, int32_t C, int64_t count, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, float* stats,
                       void* stream);
-int vsseg_bn_act_fwd(const vsseg_act8* c, const vsseg_act8* y, const float* stats, float slope, float drop_p,
+/* slope: DEVICE pointer to the PReLU parameter (act.weight, one element): read by the kernel, so a training step never
+ * copies parameters to the host and can be captured in a CUDA graph */
+int vsseg_bn_act_fwd(const vsseg_act8* c, const vsseg_act8* y, const float* stats, const float* slope, float drop_p,
                      uint64_t seed, const vsseg_act8* residual, void* stream);
-int vsseg_bn_act_bwd_reduce(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, float slope,
+int vsseg_bn_act_bwd_reduce(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const float* slope,
                             float drop_p, uint64_t seed, double* sums, void* stream);
 int vsseg_bn_act_bwd_apply(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const double* sums,
-                           float slope, float drop_p, uint64_t seed, const vsseg_act8* dc, void* stream);
+                           const float* slope, float drop_p, uint64_t seed, const vsseg_act8* dc, void* stream);
 int vsseg_act_bwd(const vsseg_act8* y, const vsseg_act8* dy, float slope, const vsseg_act8* dc, void* stream);
 int vsseg_act8_add(const vsseg_act8* a, const vsseg_act8* b, const vsseg_act8* out, void* stream);
 int vsseg_conv3d_wgrad(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_conv_geom* g, float* dw,

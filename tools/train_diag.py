@@ -1,4 +1,7 @@
-"""Per-parameter gradient error of the native training path vs torch autograd on the CPU (GPU box)."""
+"""Per-parameter gradient error of the native training path AND of torch fp32 autograd, both against torch fp64
+autograd on the CPU (GPU box): shows how much of the native error is the conditioning of the train-mode BatchNorm chain.
+usage: python tools/train_diag.py [B 1 X Y Z] ; writes gpurun_out/r2_train_grad_vs_fp64.json"""
+import json
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,3 +33,19 @@ for n, p in pr.items():
 rows = [r for r in rows if r[1] > 1e-9]
 for r in sorted(rows, reverse=True)[:30]:
     print(f"rel_err {r[0]:.3e}  torch_fp32_rel_err {r[4]:.3e}  gmax {r[1]:.3e}  proj {r[3]:.5f}  {r[2][-60:]}")
+
+import statistics
+ratio = [r[0] / max(r[4], 1e-12) for r in rows]
+summary = {"what": "max-abs gradient error per parameter tensor relative to the tensor's largest fp64 gradient entry; native (split-bf16 "
+                   "activations, fp32 accumulation) and torch fp32 CPU autograd, both against torch fp64 CPU autograd; dropout 0",
+           "shape": list(shape), "tensors": len(rows),
+           "native_rel_err": {"max": max(r[0] for r in rows), "median": statistics.median(r[0] for r in rows)},
+           "torch_fp32_rel_err": {"max": max(r[4] for r in rows), "median": statistics.median(r[4] for r in rows)},
+           "native_over_fp32": {"max": max(ratio), "median": statistics.median(ratio)},
+           "projection_min_max": [min(r[3] for r in rows), max(r[3] for r in rows)],
+           "loss_fp64": loss_r.item(), "loss_native": loss_n.item(), "loss_fp32": loss_3.item(),
+           "worst": [{"param": r[2], "native": r[0], "torch_fp32": r[4], "gmax": r[1], "proj": r[3]} for r in sorted(rows, reverse=True)[:12]]}
+os.makedirs("gpurun_out", exist_ok=True)
+tag = "x".join(str(v) for v in shape)
+json.dump(summary, open(f"gpurun_out/r2_train_grad_vs_fp64_{tag}.json", "w"), indent=1)
+print(json.dumps({k: summary[k] for k in ("native_rel_err", "torch_fp32_rel_err", "native_over_fp32", "projection_min_max")}))

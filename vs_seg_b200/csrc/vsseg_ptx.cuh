@@ -111,6 +111,30 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
 }
+// A operand from tensor memory ("TS"): D[tmem] += A[tmem: 128 lanes x 8 columns = 128 x 16 bf16] * B[smem descriptor]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+}
+// shared memory (K-major SWIZZLE_NONE matrix descriptor: 128 rows x 32 bytes) -> tensor memory (128 lanes x 8 columns)
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint32_t s_lo, uint32_t s_hi) {
+    asm volatile(
+        "{\n"
+        ".reg .b64 ds;\n"
+        "mov.b64 ds, {%1, %2};\n"
+        "tcgen05.cp.cta_group::1.128x256b [%0], ds;\n"
+        "}\n" ::"r"(taddr),
+        "r"(s_lo), "r"(s_hi)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");

@@ -105,6 +105,13 @@ struct TcArgs {
     int partial;               // the last y line group is partial (rows beyond Ym are masked)
     vsseg_act8 gate;           // out mode 2: AttentionBlock2 gate applied in place to this tensor, x *= 1 + att
     int two_pass;              // Cout <= 2 planar output: weights packed [hi | lo] along N, two MMAs per product
+    // TS mode (k = (.,.,1) stride-1 convs on 128-long z lines): the A operand is copied once per staged plane from shared
+    // memory to tensor memory (tcgen05.cp) and every MMA reads it from there - the SS-mode MMA re-reads its 4 KB A view
+    // from shared memory on every instruction (the 32 + N/4 cycle floor), which is what bounds the narrow layers
+    int ts_mode;
+    uint32_t a_tmem_col;       // first TMEM column of the A buffers
+    uint32_t a_cols;           // columns of one A buffer: BY views x 2 planes x 8
+    int na;                    // A buffers
 };
 
 constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
@@ -124,7 +131,8 @@ constexpr int TC_EPI_WARPS = VSSEG_TC_EPI_WARPS;  // four warps per TMEM lane qu
 // tracked by one commit per issuer on every barrier.
 constexpr int TC_MMA_WARPS = VSSEG_TC_MMA_WARPS;
 constexpr int TC_EPI_WARP0 = 1 + TC_MMA_WARPS;   // first epilogue warp (a multiple of 4 plus 1: quadrant = warp % 4)
-constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);  // warp 0: producer, warps 1-4: MMA issuers (warp 1 owns TMEM), rest: epilogue
+constexpr int TC_CP_WARP = TC_EPI_WARP0 + TC_EPI_WARPS;   // TS mode: the warp that copies staged A views to tensor memory
+constexpr int TC_THREADS = 32 * (TC_CP_WARP + 1);  // warp 0: producer, warps 1-3: MMA issuers (warp 1 owns TMEM), 16 epilogue warps, copier
 constexpr int TC_MAX_SLOT = 8;    // accumulator row slots in TMEM
 
 __device__ uint4 g_zero_line[136];  // source of padding lines / halo rows for the bulk-copy producer (zero-initialised)
@@ -314,6 +322,13 @@ __device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) 
     }
 }
 
+// one MMA with the A operand from shared memory (descriptor low word) or, TS, from tensor memory (column address)
+template <bool TS>
+__device__ __forceinline__ void mma_a(uint32_t t, uint32_t a, uint32_t dh, uint32_t bl, uint32_t idesc) {
+    if constexpr (TS) umma_bf16_ts(t, a, bl, dh, idesc);
+    else umma_bf16_w(t, a, dh, bl, dh, idesc);
+}
+
 // Persistent kernel: CTA i walks tiles i, i+gridDim.x, ...  A tile is XT consecutive x rows of one
 // (y line group, z tile, Cout slice).  The CTA marches along x: every input plane is staged ONCE per
 // 16-channel chunk and feeds the (up to) three output rows that use it through the three x taps, so
@@ -322,7 +337,7 @@ __device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) 
 // by the epilogue warps while the MMA thread works on the following planes, then re-zeroed and handed
 // back.  The shared-memory ring runs across row and tile boundaries.  XT = 1 is the plain
 // one-row-per-tile schedule (strided / transposed convs, layers whose accumulators fill TMEM).
-template <int OM, bool SC, int RM>
+template <int OM, bool SC, int RM, bool TS>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ CUtensorMap tmap2,
                                                              const __grid_constant__ TcArgs a) {
@@ -332,6 +347,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     uint64_t* acc_full = full + 16;                      // [nslot]
     uint64_t* acc_empty = full + 24;                     // [nslot]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full + 32);
+    uint64_t* a_full = full + 34;                        // [na]  TS mode: A views of a stage are in tensor memory
+    uint64_t* a_empty = full + 38;                       // [na]  ... and have been consumed by every issuer
     // per-channel epilogue constants of this CTA's Cout slice(s), staged once: [scale | shift | bias2 | res_w | res_b][256]
     float* ep_c = reinterpret_cast<float*>(smem + 1024);
     const uint32_t ring = smem_u32(smem) + TC_HDR;
@@ -345,7 +362,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.nstage; ++i) {
             mbar_init(full + i, 1);
-            mbar_init(empty + i, TC_MMA_WARPS);
+            mbar_init(empty + i, TC_MMA_WARPS + (TS ? 1 : 0));   // TS: the copier's reads of the stage count too
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(a_full + i, 1);
+            mbar_init(a_empty + i, TC_MMA_WARPS);
         }
         for (int i = 0; i < TC_MAX_SLOT; ++i) {
             mbar_init(acc_full + i, TC_MMA_WARPS);
@@ -518,14 +539,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                         const int st = it % a.nstage;
                         const long long t0 = a.dbg ? clock64() : 0;
                         mbar_wait(full + st, (it / a.nstage) & 1);
+                        const int ab = TS ? it % a.na : 0;
+                        if constexpr (TS) mbar_wait(a_full + ab, (it / a.na) & 1);   // the stage's A views are in tensor memory
                         tc_fence_after();
                         if (a.dbg) { t_full += clock64() - t0; n_mma += seg2 ? a.nop2 : a.nop * (a.XT == 1 ? 1 : min(q, T.xt - 1) - max(q - njm1, 0) + 1); }   // all issuers' MMAs
                         const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
-                        const uint32_t da = (base & 0x3FFFF) >> 4, db = ((base + a.b_off) & 0x3FFFF) >> 4;   // stage start, 16 B units
+                        // A: stage start in 16 B units (descriptor low word) | TS: first column of the stage's A buffer
+                        const uint32_t da = TS ? tmem_base + a.a_tmem_col + (uint32_t)ab * a.a_cols : (base & 0x3FFFF) >> 4;
+                        const uint32_t db = ((base + a.b_off) & 0x3FFFF) >> 4;
                         const uint32_t dh = a.desc_hi;
                         const bool tp = a.two_pass != 0;   // (A_hi, [W_hi | W_lo]) and (A_lo, [W_hi | 0]) instead of three passes
                         if (!seg2) {
-                            const uint32_t ap = a.a_plane >> 4, bp = a.b_plane >> 4;
+                            const uint32_t ap = TS ? (uint32_t)a.BY * 8u : a.a_plane >> 4, bp = a.b_plane >> 4;
                             const int nel = a.nop / 3;
                             if (a.XT == 1) {
                                 const uint32_t tr = tmem_base + (uint32_t)(rowbase % R) * slot_cols;
@@ -533,12 +558,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                 for (int i = rowbase % TC_MMA_WARPS == mw ? 0 : nel; i < nel; ++i) {
                                     const TcEl e = a.el[i];
                                     const uint32_t al = e.a_lo + da, bl = e.b_lo + db, t = tr + e.col;
-                                    umma_bf16_w(t, al, dh, bl, dh, e.idesc);
+                                    mma_a<TS>(t, al, dh, bl, e.idesc);
                                     if (tp) {
-                                        umma_bf16_w(t, al + ap, dh, bl + bp, dh, e.idesc);
+                                        mma_a<TS>(t, al + ap, dh, bl + bp, e.idesc);
                                     } else {
-                                        umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
-                                        umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                        mma_a<TS>(t, al + ap, dh, bl, e.idesc);
+                                        mma_a<TS>(t, al, dh, bl + bp, e.idesc);
                                     }
                                 }
                             } else {
@@ -552,28 +577,29 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                     for (int i = 0; i < nel; ++i) {
                                         const TcEl e = a.el[i];
                                         const uint32_t al = e.a_lo + da, bl = e.b_lo + dbx, t = tr + e.col;
-                                        umma_bf16_w(t, al, dh, bl, dh, e.idesc);
+                                        mma_a<TS>(t, al, dh, bl, e.idesc);
                                         if (tp) {
-                                            umma_bf16_w(t, al + ap, dh, bl + bp, dh, e.idesc);
+                                            mma_a<TS>(t, al + ap, dh, bl + bp, e.idesc);
                                         } else {
-                                            umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
-                                            umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                            mma_a<TS>(t, al + ap, dh, bl, e.idesc);
+                                            mma_a<TS>(t, al, dh, bl + bp, e.idesc);
                                         }
                                     }
                                 }
                             }
                         } else {
-                            const uint32_t ap = a.a_plane >> 4, bp = a.b2_plane >> 4;
+                            const uint32_t ap = TS ? (uint32_t)a.BY * 8u : a.a_plane >> 4, bp = a.b2_plane >> 4;
                             const uint32_t tr = tmem_base + (uint32_t)((rowbase + rs) % R) * slot_cols + row_cols;
                             for (int i = (rowbase + rs) % TC_MMA_WARPS == mw ? 0 : a.nop2 / 3; i < a.nop2 / 3; ++i) {
                                 const TcEl e = a.el2[i];
                                 const uint32_t al = e.a_lo + da, bl = e.b_lo + db, t = tr + e.col;
-                                umma_bf16_w(t, al, dh, bl, dh, e.idesc);
-                                umma_bf16_w(t, al + ap, dh, bl, dh, e.idesc);
-                                umma_bf16_w(t, al, dh, bl + bp, dh, e.idesc);
+                                mma_a<TS>(t, al, dh, bl, e.idesc);
+                                mma_a<TS>(t, al + ap, dh, bl, e.idesc);
+                                mma_a<TS>(t, al, dh, bl + bp, e.idesc);
                             }
                         }
                         umma_commit(empty + st);
+                        if constexpr (TS) umma_commit(a_empty + ab);
                         ++it;
                     }
                     // rows whose last plane this was are complete
@@ -588,6 +614,41 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 a.dbg[blockIdx.x * 8 + 2] = (unsigned long long)(clock64() - t_beg);
                 a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)n_mma;
             }
+        }
+    } else if (warp == TC_CP_WARP) {
+        // ===== TS mode: copy the staged A views (BY lines x hi/lo planes, 128 x 16 bf16 each) from shared memory to the
+        // stage's A buffer in tensor memory.  One copy per view and staged plane replaces one 4 KB shared-memory read per
+        // MMA (an x-march plane feeds up to three rows x three passes per view).  Same walk as the producer / issuers.
+        if constexpr (TS) {
+          if (elect_one()) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const TcTile T = decode_tile(a, tile);
+                for (int q = T.q_lo; q <= T.q_hi; ++q) {
+                    const int rs = q - jc;
+                    const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                    for (int cs = 0; cs < a.nchunk + n2; ++cs) {
+                        const bool seg2 = cs >= a.nchunk;
+                        const int st = it % a.nstage, ab = it % a.na;
+                        mbar_wait(full + st, (it / a.nstage) & 1);
+                        mbar_wait(a_empty + ab, ((it / a.na) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t base = ring + (uint32_t)st * a.stage_bytes;
+                        const uint32_t tdst = tmem_base + a.a_tmem_col + (uint32_t)ab * a.a_cols;
+                        const uint32_t lbo = ((a.lbo_a >> 4) & 0x3FFFu) << 16;
+                        const int v0 = seg2 ? a.hy : 0, v1 = seg2 ? a.hy + a.YL : a.BY;   // the shortcut reads the tile's own lines
+                        for (int v = v0; v < v1; ++v) {
+                            const uint32_t sa = base + (uint32_t)v * 2048u;
+                            tmem_cp_128x256b(tdst + (uint32_t)v * 8u, (((sa) & 0x3FFFF) >> 4) | lbo, a.desc_hi);
+                            tmem_cp_128x256b(tdst + (uint32_t)(a.BY + v) * 8u, (((sa + a.a_plane) & 0x3FFFF) >> 4) | lbo, a.desc_hi);
+                        }
+                        umma_commit(a_full + ab);
+                        umma_commit(empty + st);
+                        ++it;
+                    }
+                }
+            }
+          }
         }
     } else {
         // ===== epilogue: TC_EPI_WARPS warps, TMEM lanes (warp % 4) * 32 .. +31, thread = one M-tile row;
@@ -857,7 +918,12 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     static const double fill_bpc = getenv("VSSEG_TC_FILL_BPC") ? atof(getenv("VSSEG_TC_FILL_BPC")) : 36.0;   // L2 -> shared bytes/cycle/SM
     static const double epi_unit = getenv("VSSEG_TC_EPI_UNIT") ? atof(getenv("VSSEG_TC_EPI_UNIT")) : 400.0;  // cycles per (accumulator, 16 columns) unit per warp
     int best_slots = 1;
+    bool best_ts = false;
+    // TS mode: stride-1 convs without z taps on 128-long z lines (box mode, every A view is one whole z line)
+    static const int ts_env = getenv("VSSEG_TC_TS") ? atoi(getenv("VSSEG_TC_TS")) : 1;   // 0 off, 1 cost model, 2 forced where possible
+    const bool ts_ok = ts_env != 0 && !tr && !strided && !line && KZ == 1 && LY == 1;
     const int sms_ = sm_count();
+    for (int ts = 0; ts <= (ts_ok ? 1 : 0); ++ts)
     for (int XT = 1; XT <= (xt_ok ? (xt_max < Xm ? xt_max : Xm) : 1); ++XT) {
         if (XT > 1 && XT < xt_min && xt_min <= Xm) continue;
         const int nseg = (Xm + XT - 1) / XT;
@@ -870,8 +936,12 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             if (cols1 > 512) break;
             if (YT * acc_mult > TC_MAX_ACC) break;
             // row slots: XT = 1 double-buffers whole tiles when two fit; the x march needs the three
-            // rows a plane feeds plus (ideally) one being drained
-            int slots = 512 / cols1;
+            // rows a plane feeds plus (ideally) one being drained.  TS: two A buffers of BY views x 2 planes x 8
+            // columns come out of the same 512 columns
+            const int by_ts = (YT - 1) * sy_in + KY;
+            const int acc_cols = ts ? 512 - 2 * 16 * by_ts : 512;
+            if (acc_cols < cols1) break;
+            int slots = acc_cols / cols1;
             if (XT == 1) slots = slots >= 2 ? 2 : 1;
             else if (slots < 3) continue;
             else if (slots > 6) slots = 6;
@@ -892,11 +962,16 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
                 static TcAcc scratch_acc[TC_MAX_ACC];
                 int n1 = 0, n2 = 0;
                 if (!gen_ops(G, YT, scratch, &n1, scratch_acc, &n2) || (src2 && YT * 3 > TC_MAX_OPS2)) break;
+                double b_rd = 0;
                 for (int i = 0; i < n1; ++i) {   // SS-mode MMA cost, measured (tools/ubench/mma_rate.cu)
                     const double N = scratch[i].n8 * 8.0;
-                    mma_cyc += N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
+                    if (ts) { mma_cyc += N / 2 > 16 ? N / 2 : 16; b_rd += N * 32; }   // TS: N/2 cycles, only B comes from shared memory
+                    else mma_cyc += N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
                 }
+                if (ts && b_rd / 128 > mma_cyc) mma_cyc = b_rd / 128;
             }
+            // TS: the copies read every staged view once more from shared memory (128 B/cycle)
+            const double cp_cyc = ts ? (double)(2 * a_plane) / 128.0 : 0.0;
             const size_t stage = 2 * a_plane + bstage;
             if (stage / 16 >= 16000) break;
             const long budget = 227L * 1024 - TC_HDR;
@@ -910,7 +985,7 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             // a stage can only be refilled after its MMAs have drained: with a 2-deep ring the copy latency
             // (~1500 cycles issue-to-arrival) is exposed on every stage, with 3+ it hides behind the other stages
             static const double fill_lat = getenv("VSSEG_TC_FILL_LAT") ? atof(getenv("VSSEG_TC_FILL_LAT")) : 0.0;   // measured: a latency term makes the choice worse overall
-            const double fill_cyc = (double)stage / fill_bpc + (nst == 2 ? fill_lat : 0.0);
+            const double fill_cyc = (double)stage / fill_bpc + (nst == 2 ? fill_lat : 0.0) + cp_cyc;
             double main_cyc;
             if (XT > 1) {
                 const double per_plane = 3.0 * XT / (XT + 2) * mma_cyc;   // x taps served per staged plane, on average
@@ -929,9 +1004,10 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             const double tile_cyc = overlap ? (main_cyc > epi_cyc ? main_cyc : epi_cyc) + 300.0
                                             : main_cyc + epi_cyc + (XT == 1 ? 1500.0 : 0.0);
             const double cost = (double)((tiles + sms_ - 1) / sms_) * tile_cyc + 4000.0;
-            if (cost < best_cost) {
+            if (cost < best_cost || (ts_env == 2 && ts && !best_ts)) {
                 best_cost = cost; best = YT; best_xt = XT; best_stage = stage; best_slots = slots;
                 best_nstage = nst > 6 ? 6 : nst;
+                best_ts = ts != 0;
             }
         }
     }
@@ -982,6 +1058,10 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     a.BY = BY; a.pitch = BZ; a.hy = tr ? 0 : hy; a.hz = hz; a.Yin = in->Y; a.Zin = in->Z;
     a.in = *in;
     if (src2) a.in2 = *src2;
+    a.ts_mode = best_ts ? 1 : 0;
+    a.na = 2;
+    a.a_cols = (uint32_t)(16 * BY);
+    a.a_tmem_col = 512u - 2u * a.a_cols;
     // boxes
     for (int i = 0; i < nbox; ++i) {
         TcBox& bx = a.boxes[i];
@@ -1018,15 +1098,16 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
         // descriptor words (sm_100 K-major SWIZZLE_NONE: start >> 4 | LBO >> 4 << 16 ; SBO >> 4 | version 1 << 14).
         // gen_ops emits the three passes of a merged product back to back; pass 0 carries the plane-0 offsets
         a.desc_hi = (128u >> 4) | (1u << 14);
+        // TS mode: the A word is the view's first column inside the stage's A buffer (a view = one 2 KB z line)
         for (int i = 0; i < a.nop / 3; ++i) {
             const TcOp& o = a.ops[3 * i];
-            a.el[i] = {o.a16 + (((a.lbo_a >> 4) & 0x3FFFu) << 16), o.b16 + (((a.lbo_b >> 4) & 0x3FFFu) << 16), o.col,
-                       a.idesc | ((uint32_t)o.n8 << 17)};
+            const uint32_t aw = a.ts_mode ? (uint32_t)(o.a16 / 128) * 8u : o.a16 + (((a.lbo_a >> 4) & 0x3FFFu) << 16);
+            a.el[i] = {aw, o.b16 + (((a.lbo_b >> 4) & 0x3FFFu) << 16), o.col, a.idesc | ((uint32_t)o.n8 << 17)};
         }
         for (int i = 0; i < a.nop2 / 3; ++i) {
             const TcOp& o = a.ops2[3 * i];
-            a.el2[i] = {o.a16 + (((a.lbo_a >> 4) & 0x3FFFu) << 16), o.b16 + (((a.lbo_b2 >> 4) & 0x3FFFu) << 16), o.col,
-                        a.idesc | ((uint32_t)o.n8 << 17)};
+            const uint32_t aw = a.ts_mode ? (uint32_t)(o.a16 / 128) * 8u : o.a16 + (((a.lbo_a >> 4) & 0x3FFFu) << 16);
+            a.el2[i] = {aw, o.b16 + (((a.lbo_b2 >> 4) & 0x3FFFu) << 16), o.col, a.idesc | ((uint32_t)o.n8 << 17)};
         }
         a.partial = (Ym % LY) != 0 ? 1 : 0;
         for (int i = 0; i < a.nacc; ++i) a.accs[i].off8 = (a.accs[i].y_add * out->Z + a.accs[i].z_add) * 8;
@@ -1036,7 +1117,7 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     const int cols1 = nacc * (src2 ? 2 : 1) * n_cta;
     a.nbuf = best_slots;   // TMEM row slots
     const int cols = cols1 * a.nbuf;
-    a.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    a.tmem_cols = a.ts_mode ? 512 : cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     P->box[0] = 8; P->box[1] = (cuuint32_t)(BZ * (strided ? g->sz : 1)); P->box[2] = (cuuint32_t)(BY * (strided ? g->sy : 1));
     P->box[3] = 1; P->box[4] = 2;
     P->estr[0] = 1; P->estr[1] = (cuuint32_t)(strided ? g->sz : 1); P->estr[2] = (cuuint32_t)(strided ? g->sy : 1);
@@ -1131,18 +1212,24 @@ static int encode_map(CUtensorMap* tmap, const vsseg_act8* t, int cg_plane, int 
 
 // epilogue flavours are compile-time (out mode, fused shortcut, residual mode): the dead paths cost registers
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcArgs);
-static TcKernel pick_kernel(const TcArgs& a) {
+template <bool TS>
+static TcKernel pick_kernel_ts(const TcArgs& a) {
     const bool sc = a.nchunk2 != 0;
-    if (a.out_mode == 2) return conv_tc_kernel<2, false, 0>;
-    if (a.out_mode == 1) return conv_tc_kernel<1, false, 0>;
-    if (sc) return a.res_mode == 0 ? conv_tc_kernel<0, true, 0> : a.res_mode == 1 ? conv_tc_kernel<0, true, 1> : conv_tc_kernel<0, true, 2>;
-    return a.res_mode == 0 ? conv_tc_kernel<0, false, 0> : a.res_mode == 1 ? conv_tc_kernel<0, false, 1> : conv_tc_kernel<0, false, 2>;
+    if (a.out_mode == 2) return conv_tc_kernel<2, false, 0, TS>;
+    if (a.out_mode == 1) return conv_tc_kernel<1, false, 0, TS>;
+    if (sc) return a.res_mode == 0 ? conv_tc_kernel<0, true, 0, TS> : a.res_mode == 1 ? conv_tc_kernel<0, true, 1, TS> : conv_tc_kernel<0, true, 2, TS>;
+    return a.res_mode == 0 ? conv_tc_kernel<0, false, 0, TS> : a.res_mode == 1 ? conv_tc_kernel<0, false, 1, TS> : conv_tc_kernel<0, false, 2, TS>;
 }
+static TcKernel pick_kernel(const TcArgs& a) { return a.ts_mode ? pick_kernel_ts<true>(a) : pick_kernel_ts<false>(a); }
 static int set_smem_attr() {
     static bool attr_set = false;
     if (!attr_set) {
-        const TcKernel all[] = {conv_tc_kernel<2, false, 0>, conv_tc_kernel<1, false, 0>, conv_tc_kernel<0, true, 0>, conv_tc_kernel<0, true, 1>, conv_tc_kernel<0, true, 2>,
-                                conv_tc_kernel<0, false, 0>, conv_tc_kernel<0, false, 1>, conv_tc_kernel<0, false, 2>};
+        const TcKernel all[] = {conv_tc_kernel<2, false, 0, false>, conv_tc_kernel<1, false, 0, false>, conv_tc_kernel<0, true, 0, false>,
+                                conv_tc_kernel<0, true, 1, false>, conv_tc_kernel<0, true, 2, false>, conv_tc_kernel<0, false, 0, false>,
+                                conv_tc_kernel<0, false, 1, false>, conv_tc_kernel<0, false, 2, false>,
+                                conv_tc_kernel<2, false, 0, true>, conv_tc_kernel<1, false, 0, true>, conv_tc_kernel<0, true, 0, true>,
+                                conv_tc_kernel<0, true, 1, true>, conv_tc_kernel<0, true, 2, true>, conv_tc_kernel<0, false, 0, true>,
+                                conv_tc_kernel<0, false, 1, true>, conv_tc_kernel<0, false, 2, true>};
         for (TcKernel k : all) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) {
@@ -1276,11 +1363,11 @@ int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const 
     int n = snprintf(buf, buflen,
                      "grid=%u smem=%zu nstage=%d stage_bytes=%u line_mode=%d LZ=%d LY=%d YL=%d BY=%d pitch=%d nbox=%d "
                      "box=[%u,%u,%u,%u,%u] estr=[%u,%u] box_tx=%u a_plane=%u b_off=%u b_bytes=%u lbo_a=%u lbo_b=%u nacc=%d "
-                     "n_cta=%d tmem_cols=%u nchunk=%d nj=%d nchunk2=%d nop=%d nop2=%d ntx=%d nty=%d ntz=%d nsel=%d ops:",
+                     "n_cta=%d tmem_cols=%u nchunk=%d nj=%d nchunk2=%d nop=%d nop2=%d ntx=%d nty=%d ntz=%d nsel=%d XT=%d slots=%d ts=%d ops:",
                      P.grid, P.smem, a.nstage, a.stage_bytes, a.line_mode, a.LZ, a.LY, a.YL, a.BY, a.pitch, a.nbox, P.box[0],
                      P.box[1], P.box[2], P.box[3], P.box[4], P.estr[1], P.estr[2], a.box_tx, a.a_plane, a.b_off, a.b_bytes,
                      a.lbo_a, a.lbo_b, a.nacc, a.n_cta, a.tmem_cols, a.nchunk, a.nj, a.nchunk2, a.nop, a.nop2, a.ntx, a.nty,
-                     a.ntz, a.nsel);
+                     a.ntz, a.nsel, a.XT, a.nbuf, a.ts_mode);
     for (int i = 0; i < a.nop && n < buflen - 40; ++i)
         n += snprintf(buf + n, buflen - n, " (a%u b%u c%u n%u)", a.ops[i].a16, a.ops[i].b16, a.ops[i].col, a.ops[i].n8 * 8);
     return 0;

@@ -84,11 +84,11 @@ _SIGNATURES = {
     "vsseg_bn_stats": (C.c_int, [_P(Act8), C.c_void_p, C.c_void_p]),
     "vsseg_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "vsseg_bn_act_fwd": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_float, C.c_float, C.c_uint64, _P(Act8),
+    "vsseg_bn_act_fwd": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, _P(Act8),
                                    C.c_void_p]),
-    "vsseg_bn_act_bwd_reduce": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_float, C.c_float, C.c_uint64, C.c_void_p,
+    "vsseg_bn_act_bwd_reduce": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p,
                                           C.c_void_p]),
-    "vsseg_bn_act_bwd_apply": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_uint64,
+    "vsseg_bn_act_bwd_apply": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64,
                                          _P(Act8), C.c_void_p]),
     "vsseg_act_bwd": (C.c_int, [_P(Act8), _P(Act8), C.c_float, _P(Act8), C.c_void_p]),
     "vsseg_act8_add": (C.c_int, [_P(Act8), _P(Act8), _P(Act8), C.c_void_p]),

@@ -50,14 +50,7 @@ class UNetTrainStep:
         self.stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.tape = []
         self._consts = {}
-        # PReLU slopes are kernel arguments: read ALL of them with one device->host copy per step (reading them
-        # block by block was a host sync in front of every Convolution block: the forward pass could never run ahead)
-        names = [n for n in dict(model.named_parameters()) if n.endswith("act.weight")]
-        if names:
-            vals = torch.cat([dict(model.named_parameters())[n].detach().reshape(-1)[:1] for n in names]).tolist()
-            self._slopes = dict(zip(names, vals))
-        else:
-            self._slopes = {}
+        # PReLU slopes are read by the kernels through device pointers (act.weight): the step never syncs the host
         self.keep = []
         self.pgrads = {}          # parameter name -> fp32 grad tensor (torch layout)
         self.p = dict(model.named_parameters())
@@ -194,7 +187,9 @@ class UNetTrainStep:
         w, bias = self.p[prefix + "conv.weight"], self.p[prefix + "conv.bias"]
         gamma, beta = self.p[prefix + "norm.weight"], self.p[prefix + "norm.bias"]
         slope_t = self.p[prefix + "act.weight"]
-        slope = self._slopes[prefix + "act.weight"]
+        if slope_t.dtype != torch.float32 or slope_t.numel() != 1:
+            raise NotImplementedError("native training covers PReLU with one shared fp32 slope (the reference's Act.PRELU)")
+        slope = slope_t.data_ptr()
         Cc = dst.C
         cbuf = Act8Buffer(dst.B, Cc, dst.X, dst.Y, dst.Z, self.dev)
         self.keep.append(cbuf)
