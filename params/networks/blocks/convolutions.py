@@ -98,8 +98,15 @@ class Convolution(nn.Sequential):
 
         if self.training and (self._norm_name is not None or "dropout" in self._modules):
             raise NotImplementedError(
-                "train-mode BatchNorm/Dropout of a standalone Convolution block has no native kernel yet; "
-                "call .eval() (there is no eager CUDA fallback)")
+                "train-mode BatchNorm/Dropout of a standalone Convolution block has no native kernel; the native "
+                "training path is the whole-network step (UNet2d5_spvPA.forward in train mode, vs_seg_b200.training); "
+                "call .eval() for the fused inference block (there is no eager CUDA fallback)")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the fused inference kernel runs outside autograd: its output would carry no grad_fn and the
+            # parameters would silently receive no gradient
+            raise NotImplementedError(
+                "a standalone Convolution block in train mode with gradients enabled has no native backward; "
+                "use torch.no_grad() / .eval(), or train through UNet2d5_spvPA")
         if not self._native_supported():
             raise NotImplementedError("this Convolution configuration has no native sm_100a kernel")
         c = self.conv

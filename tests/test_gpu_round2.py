@@ -251,6 +251,44 @@ def test_dice_loss_native_shape_mismatch_raises():
         DiceLoss()(torch.zeros(1, 1, 4, 4, 4, device=_dev()), torch.zeros(1, 1, 4, 4, 5, device=_dev()))
 
 
+def test_fused_adam_state_dict_carries_the_flat_moments():
+    import copy
+    from vs_seg_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    ws = [torch.nn.Parameter(torch.randn(7, 3, device=_dev())), torch.nn.Parameter(torch.randn(5, device=_dev()))]
+    vs = [torch.nn.Parameter(w.detach().clone()) for w in ws]
+    a, b = FusedAdam(ws, lr=1e-2, weight_decay=1e-3), FusedAdam(vs, lr=1e-2, weight_decay=1e-3)
+    g = [[torch.randn_like(w) for w in ws] for _ in range(4)]
+    for i in range(2):
+        a.zero_grad()
+        for w, gi in zip(ws, g[i]):
+            w.grad.copy_(gi)
+        a.step()
+    sd = copy.deepcopy(a.state_dict())
+    with torch.no_grad():
+        for v, w in zip(vs, ws):
+            v.copy_(w)
+    b.load_state_dict(sd)
+    for i in range(2, 4):
+        for opt, ps in ((a, ws), (b, vs)):
+            opt.zero_grad()
+            for w, gi in zip(ps, g[i]):
+                w.grad.copy_(gi)
+            opt.step()
+    for v, w in zip(vs, ws):
+        assert torch.equal(v.data, w.data)
+
+
+def test_standalone_convolution_in_train_mode_with_grad_raises():
+    from params.networks.blocks.convolutions import Convolution
+    blk = Convolution(3, 16, 8, kernel_size=(3, 3, 1), act="RELU", norm=None, dropout=None).to(_dev()).train()
+    x = torch.randn(1, 16, 8, 8, 8, device=_dev())
+    with pytest.raises(NotImplementedError):
+        blk(x)
+    with torch.no_grad():
+        assert blk(x).shape == (1, 8, 8, 8, 8)
+
+
 # ---- two ranks over NCCL ----------------------------------------------------------------------------------------
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
 def test_two_rank_nccl_sharded_inference_equals_one_gpu(tmp_path):

@@ -117,6 +117,29 @@ def test_fused_adam_on_cpu_is_torch_adam():
     assert oa.flat_grads() == []
 
 
+def test_fused_adam_state_dict_round_trip_on_cpu():
+    """state_dict / load_state_dict carry the moments and step counters (a resumed run must not restart at zero)."""
+    from vs_seg_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    w1, w2 = torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(5, 3))
+    w2.data.copy_(w1.data)
+    a, b = FusedAdam([w1], lr=1e-2, weight_decay=1e-3), FusedAdam([w2], lr=1e-2, weight_decay=1e-3)
+    g = torch.randn(4, 5, 3)
+    for i in range(2):
+        w1.grad = g[i].clone()
+        a.step()
+    import copy
+    sd = copy.deepcopy(a.state_dict())   # as torch.save / torch.load would (state_dict() hands out references)
+    assert sd["param_groups"][0]["step"] == 2 and "fused" in sd and "cpu" in sd
+    w2.data.copy_(w1.data)
+    b.load_state_dict(sd)
+    for i in range(2, 4):
+        w1.grad, w2.grad = g[i].clone(), g[i].clone()
+        a.step()
+        b.step()
+    assert torch.equal(w1.data, w2.data)
+
+
 def test_nifti_saver_restores_the_original_orientation(tmp_path):
     """NiftiSaver must undo Orientationd(RAS) before writing under the file's original affine (reference
     VSparams.py:582-594 passes affine AND original_affine to MONAI's NiftiSaver): LPS-ordered files (negative

@@ -77,6 +77,28 @@ class FusedAdam(torch.optim.Optimizer):
             p.grad = g
             off += (p.numel() + 3) // 4 * 4
 
+    def state_dict(self):
+        """torch's state_dict plus the fused moments: a resumed run continues with the same exp_avg / exp_avg_sq
+        (the step counters travel in param_groups), CPU groups carry their torch.optim.Adam state."""
+        sd = super().state_dict()
+        sd["fused"] = [None if fl is None else {"exp_avg": fl["m"].detach().clone(), "exp_avg_sq": fl["v"].detach().clone()}
+                       for fl in self._flat]
+        sd["cpu"] = [None if opt is None else opt.state_dict() for opt in self._cpu_opt]
+        return sd
+
+    def load_state_dict(self, state_dict):
+        sd = dict(state_dict)
+        fused, cpu = sd.pop("fused", None), sd.pop("cpu", None)
+        super().load_state_dict(sd)
+        for i, fl in enumerate(self._flat):
+            if fl is not None and fused is not None and fused[i] is not None:
+                if fused[i]["exp_avg"].numel() != fl["n"]:
+                    raise ValueError("FusedAdam.load_state_dict: flat moment size differs from this model's parameters")
+                fl["m"].copy_(fused[i]["exp_avg"])
+                fl["v"].copy_(fused[i]["exp_avg_sq"])
+            if fl is None and cpu is not None and cpu[i] is not None:
+                self._cpu_opt[i].load_state_dict(cpu[i])
+
     def flat_grads(self):
         """The flat gradient buffers (one per CUDA group): what a data-parallel run all-reduces."""
         return [fl["g"] for fl in self._flat if fl is not None]
