@@ -96,11 +96,14 @@ class Convolution(nn.Sequential):
         """Eval-mode fused block on CUDA: pack -> conv+BN+act(+residual) -> unpack."""
         from vs_seg_b200.engine import conv_block_ncdhw
 
+        if self.training and residual is None and self._norm_name == "BATCH" and self._act_name == "PRELU":
+            # train mode (batch-statistics BatchNorm, dropout, autograd) on the native training kernels
+            from vs_seg_b200.training import block_train_forward
+            return block_train_forward(self, x)
         if self.training and (self._norm_name is not None or "dropout" in self._modules):
             raise NotImplementedError(
-                "train-mode BatchNorm/Dropout of a standalone Convolution block has no native kernel; the native "
-                "training path is the whole-network step (UNet2d5_spvPA.forward in train mode, vs_seg_b200.training); "
-                "call .eval() for the fused inference block (there is no eager CUDA fallback)")
+                "this train-mode Convolution configuration has no native kernel (covered: BatchNorm + PReLU blocks, "
+                "channels % 8 == 0); call .eval() for the fused inference block (there is no eager CUDA fallback)")
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # the fused inference kernel runs outside autograd: its output would carry no grad_fn and the
             # parameters would silently receive no gradient
@@ -168,6 +171,9 @@ class ResidualUnit(nn.Module):
 
     def _native_forward(self, x):
         from vs_seg_b200.engine import native_shortcut
+        if self.training:   # batch-statistics BatchNorm / dropout / autograd: the native training tape of the unit
+            from vs_seg_b200.training import block_train_forward
+            return block_train_forward(self, x)
         res = x if isinstance(self.residual, nn.Identity) else native_shortcut(self.residual, x)
         cx = x
         units = list(self.conv.children())

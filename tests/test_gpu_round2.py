@@ -289,6 +289,50 @@ def test_standalone_convolution_in_train_mode_with_grad_raises():
         assert blk(x).shape == (1, 8, 8, 8, 8)
 
 
+@pytest.mark.parametrize("kind,cin,cout,k,stride,transposed,dims", [
+    ("conv", 16, 32, (3, 3, 3), (1, 1, 1), False, (8, 8, 128)),
+    ("conv", 32, 32, (3, 3, 1), (2, 2, 1), False, (8, 8, 128)),
+    ("conv", 48, 32, (3, 3, 3), (2, 2, 2), True, (4, 4, 64)),
+    ("ru", 32, 48, (3, 3, 3), (1, 1, 1), False, (8, 8, 128)),
+])
+def test_standalone_blocks_train_mode_match_torch_autograd(kind, cin, cout, k, stride, transposed, dims):
+    """Train-mode standalone Convolution / ResidualUnit on CUDA (reference convolutions.py:148-156, :209-255 under
+    autograd): batch-statistics BatchNorm, PReLU, running-stat update and every gradient vs the same module on the CPU
+    (dropout 0: masks cannot be matched).  Tolerances as test_unet_train_step_matches_torch_autograd."""
+    import copy
+    from params.networks.blocks.convolutions import Convolution, ResidualUnit
+    torch.manual_seed(cin + cout)
+    if kind == "conv":
+        ref = Convolution(3, cin, cout, strides=stride, kernel_size=k, act="PRELU", norm="BATCH", dropout=0.0,
+                          is_transposed=transposed)
+    else:
+        ref = ResidualUnit(3, cin, cout, strides=1, kernel_size=k, subunits=2, act="PRELU", norm="BATCH", dropout=0.0)
+    nat = copy.deepcopy(ref).to(_dev()).train()
+    ref.train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, cin) + dims, generator=g)
+    xr = x.clone().requires_grad_(True)
+    xn = x.to(_dev()).requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    yn = nat(xn)
+    yn.backward(gy.to(_dev()))
+    assert yn.shape == yr.shape
+    assert (yn.detach().cpu() - yr.detach()).abs().max().item() < 2e-3 * max(1.0, yr.abs().max().item())
+    gmax_x = xr.grad.abs().max().item()
+    assert (xn.grad.cpu() - xr.grad).abs().max().item() < 3e-2 * gmax_x
+    pr, pn = dict(ref.named_parameters()), dict(nat.named_parameters())
+    gmax_all = max(p.grad.abs().max().item() for p in pr.values())
+    for name, p in pr.items():
+        assert pn[name].grad is not None, name
+        err = (pn[name].grad.cpu() - p.grad).abs().max().item()
+        rel = 6e-2 if p.numel() == 1 else 3e-2
+        assert err < rel * p.grad.abs().max().item() + 1e-4 * gmax_all, (name, err)
+    for (n1, b1), (_, b2) in zip(ref.named_buffers(), nat.named_buffers()):
+        assert (b2.cpu().float() - b1.float()).abs().max().item() < 1e-4 * max(1.0, b1.float().abs().max().item()), n1
+
+
 # ---- two ranks over NCCL ----------------------------------------------------------------------------------------
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
 def test_two_rank_nccl_sharded_inference_equals_one_gpu(tmp_path):

@@ -86,7 +86,74 @@ def main():
         xcl = xin.to(memory_format=torch.channels_last_3d)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             res["cudnn_bf16_channels_last_ms"] = time_fn(lambda: blk_cl(xcl))
+    res["train"] = train_leg(net, dev, blk)
     print(json.dumps(res))
+
+
+def train_leg(net, dev, blk):
+    """Backward leg of configs[1]: the same ResidualUnit in TRAIN mode (batch-stat BatchNorm, dropout 0.1, PReLU) -
+    native forward tape + backward (tcgen05 data gradients and weight gradients, BN/PReLU backward) vs torch/cuDNN
+    autograd.  The native numbers are CUDA-event times around UNetTrainStep.residual_unit and its backward closure."""
+    from vs_seg_b200.tensors import Act8Buffer
+    from vs_seg_b200.training import UNetTrainStep, _GradBuf
+    B, dims = 2, (32, 32, 128)
+    prefix = "model.1.submodule.1.1.submodule.1.0."
+    net.train()
+    x1 = torch.randn((B, 1) + bench.ROI, device=dev)
+    xin = torch.randn((B, 32) + dims, device=dev)
+    dout_t = torch.randn((B, 48) + dims, device=dev)
+    out = {}
+
+    def once():
+        st = UNetTrainStep(net, x1)
+        src = Act8Buffer(B, 32, *dims, dev).from_ncdhw(xin)
+        gsrc = _GradBuf(src)
+        dst = Act8Buffer(B, 48, *dims, dev)
+        dout = Act8Buffer(B, 48, *dims, dev).from_ncdhw(dout_t)
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        bw = st.residual_unit(prefix, src.view(), gsrc, dst, 0, 48, (3, 3, 3), 2)
+        e[1].record()
+        bw(dout.view())
+        e[2].record()
+        torch.cuda.synchronize()
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+
+    for _ in range(2):
+        once()
+    runs = [once() for _ in range(5)]
+    out["native_fwd_ms"] = sorted(r[0] for r in runs)[len(runs) // 2]
+    out["native_bwd_ms"] = sorted(r[1] for r in runs)[len(runs) // 2]
+    out["note"] = ("native times include the host issuing the ~25 launches of the tape (CUDA events on the stream); "
+                   "fwd = conv x3 + BN stats/finalise/apply x2, bwd = BN/PReLU backward + wgrad + dgrad per conv")
+    net.eval()
+    blk = blk.float().train()
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.momentum = 0.1
+    xg = xin.clone().requires_grad_(True)
+
+    def eager():
+        y = blk(xg)
+        y.backward(dout_t)
+
+    for name, tf32, cast in (("cudnn_fp32", False, None), ("cudnn_tf32", True, None), ("cudnn_bf16_autocast", True, torch.bfloat16)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            if cast is None:
+                out[name + "_fwd_bwd_ms"] = time_fn(eager, n=10)
+            else:
+                def eager_cast():
+                    with torch.autocast("cuda", dtype=cast):
+                        y = blk(xg)
+                    y.backward(dout_t.to(y.dtype))
+                out[name + "_fwd_bwd_ms"] = time_fn(eager_cast, n=10)
+        except Exception as e:  # noqa: BLE001
+            out[name + "_error"] = repr(e)[:200]
+    out["native_fwd_bwd_ms"] = out["native_fwd_ms"] + out["native_bwd_ms"]
+    return out
 
 
 if __name__ == "__main__":

@@ -539,3 +539,89 @@ def unet_train_forward(model, x):
     names = tuple(n for n, _ in named)
     outs = _UNetTrainFn.apply(model, x, names, *[p for _, p in named])
     return outs[0], list(outs[1:])
+
+
+# ---- standalone blocks in train mode (reference convolutions.py:148-156, :209-255 under autograd) ------------------
+class _BlockHost:
+    """What UNetTrainStep needs from its `model` when the model is a single Convolution / ResidualUnit."""
+
+    def __init__(self, module, drop_p):
+        self._m, self.dropout = module, drop_p
+
+    def named_parameters(self):
+        return self._m.named_parameters()
+
+    def named_buffers(self):
+        return self._m.named_buffers()
+
+
+def _block_drop_p(module):
+    for m in module.modules():
+        if isinstance(m, torch.nn.Dropout):
+            return float(m.p)
+    return 0.0
+
+
+class _BlockTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, kind, names, *params):
+        B, cin = x.shape[:2]
+        step = UNetTrainStep(_BlockHost(module, _block_drop_p(module)), x)
+        src = Act8Buffer(B, cin, *x.shape[2:], x.device).from_ncdhw(x.detach())
+        gsrc = _GradBuf(src) if ctx.needs_input_grad[1] else None
+        if kind == "conv":
+            c = module.conv
+            cout = c.out_channels
+            odims = [d * s for d, s in zip(x.shape[2:], c.stride)] if module.is_transposed else \
+                [(d + s - 1) // s for d, s in zip(x.shape[2:], c.stride)]
+            dst = Act8Buffer(B, cout, *odims, x.device)
+            bw = step.convolution("", src.view(), gsrc, dst.view(), tuple(c.kernel_size), tuple(c.stride), module.is_transposed)
+        else:
+            units = list(module.conv.children())
+            c = units[0].conv
+            cout = module.out_channels
+            dst = Act8Buffer(B, cout, *x.shape[2:], x.device)
+            bw = step.residual_unit("", src.view(), gsrc, dst, 0, cout, tuple(c.kernel_size), len(units))
+        ctx.step, ctx.bw, ctx.gsrc, ctx.names, ctx.oshape = step, bw, gsrc, names, (B, cout, dst.X, dst.Y, dst.Z)
+        ctx.keep = (src, dst)
+        return dst.to_ncdhw()
+
+    @staticmethod
+    def backward(ctx, gy):
+        B, cout, X, Y, Z = ctx.oshape
+        dout = Act8Buffer(B, cout, X, Y, Z, gy.device).from_ncdhw(gy.contiguous())
+        ctx.bw(dout.view())
+        grads = ctx.step.pgrads
+        gx = ctx.gsrc.buf.to_ncdhw() if ctx.gsrc is not None else None
+        out = [grads.get(n) for n in ctx.names]
+        ctx.step = ctx.bw = None
+        return (None, gx, None, None, *out)
+
+
+def block_train_forward(module, x):
+    """Train-mode forward of a standalone ``Convolution`` (Conv -> BatchNorm3d(batch statistics) -> Dropout -> PReLU)
+    or ``ResidualUnit`` on CUDA through the native training kernels, differentiable w.r.t. the block's parameters and
+    its input.  Covers the block types the network is made of: 3-D, BatchNorm + PReLU, channels % 8 == 0, stride-1
+    ResidualUnits with a 1x1x1 shortcut; anything else raises (there is no eager CUDA fallback)."""
+    from params.networks.blocks.convolutions import Convolution, ResidualUnit
+    if not x.is_cuda:
+        raise _lib.NativeLibraryError("block_train_forward needs a CUDA tensor (no CPU fallback)")
+
+    def conv_ok(m):
+        return (isinstance(m, Convolution) and m._native_supported() and m._norm_name == "BATCH" and m._act_name == "PRELU"
+                and m.conv.in_channels % 8 == 0 and m.conv.out_channels % 8 == 0 and m.conv.bias is not None)
+
+    if isinstance(module, Convolution):
+        ok, kind = conv_ok(module), "conv"
+    elif isinstance(module, ResidualUnit):
+        units = list(module.conv.children())
+        ok = (len(units) in (1, 2) and all(conv_ok(u) and tuple(u.conv.stride) == (1, 1, 1) and not u.is_transposed for u in units)
+              and isinstance(module.residual, torch.nn.Conv3d) and tuple(module.residual.kernel_size) == (1, 1, 1))
+        kind = "ru"
+    else:
+        ok, kind = False, ""
+    if not ok:
+        raise NotImplementedError("native train-mode blocks: Convolution / ResidualUnit with BatchNorm + PReLU, "
+                                  "channels % 8 == 0 (ResidualUnit: stride 1, 1x1x1 shortcut)")
+    named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+    return _BlockTrainFn.apply(module, x.float(), kind, tuple(n for n, _ in named), *[p for _, p in named])
