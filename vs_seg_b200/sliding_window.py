@@ -181,7 +181,8 @@ class _Program:
             self._issue()
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # thread_local: other threads of the process (NCCL's watchdog polls events) must not abort the capture
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self._issue()
 
     @staticmethod
