@@ -333,6 +333,17 @@ def test_standalone_blocks_train_mode_match_torch_autograd(kind, cin, cout, k, s
         assert (b2.cpu().float() - b1.float()).abs().max().item() < 1e-4 * max(1.0, b1.float().abs().max().item()), n1
 
 
+def test_ts_mode_conv_parity_in_a_subprocess():
+    """The TS flavour of the tensor-core kernel (A operand staged in tensor memory with tcgen05.cp, default off because it
+    is slower on this network) stays correct: the conv / fused-shortcut / whole-net parity tests with VSSEG_TC_TS=2."""
+    env = dict(os.environ, VSSEG_TC_TS="2")
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "--no-header",
+           "-k", "tcgen05_conv or fused_shortcut or unet_eval_matches_reference_golden", "-p", "no:cacheprovider"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 # ---- two ranks over NCCL ----------------------------------------------------------------------------------------
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
 def test_two_rank_nccl_sharded_inference_equals_one_gpu(tmp_path):

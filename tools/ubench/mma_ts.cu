@@ -122,6 +122,63 @@ __global__ void check_kernel(float* out_ss, float* out_ts, long long* cyc) {
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
 }
 
+// unrolled issue loops (8 MMAs per iteration, rotating accumulators): execution rate of SS vs TS MMAs
+template <int N, bool TS, int NACC>
+__global__ void rate_kernel(int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tptr;
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3f803f80u;
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tptr;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+        const uint64_t da = make_desc(smem_u32(smem) + A_OFF, A_LBO, 128);
+        const uint64_t db = make_desc(smem_u32(smem) + B_OFF, N * 16, 128);
+        const uint32_t a_t = tb + 448;
+        for (int v = 0; v < 8; ++v) tmem_cp_128x256b(a_t + v * 8, da);
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t d = tb + (uint32_t)((u % NACC) * N);
+                if (TS) umma_ts(d, a_t + (uint32_t)(u * 8), db, idesc, 1u);
+                else umma_ss(d, da + (uint64_t)(u * 8), db, idesc, 1u);
+            }
+        }
+        commit(&bar);
+        long long t1 = clock64();
+        wait(&bar, 0);
+        long long t2 = clock64();
+        out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+template <int N, int NACC>
+void run_rate(long long* d) {
+    long long h[2], g[2];
+    const int iters = 256;
+    cudaFuncSetAttribute(rate_kernel<N, false, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(rate_kernel<N, true, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    rate_kernel<N, false, NACC><<<1, 128, 64 * 1024>>>(iters, d);
+    cudaDeviceSynchronize(); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    rate_kernel<N, true, NACC><<<1, 128, 64 * 1024>>>(iters, d);
+    cudaError_t e = cudaDeviceSynchronize(); cudaMemcpy(g, d, 16, cudaMemcpyDeviceToHost);
+    printf("rate N=%3d nacc=%d : SS issue %.1f complete %.1f | TS issue %.1f complete %.1f cycles/MMA (N/2 = %d, 32+N/4 = %d) %s\n", N, NACC,
+           h[0] / (iters * 8.0), h[1] / (iters * 8.0), g[0] / (iters * 8.0), g[1] / (iters * 8.0), N / 2, 32 + N / 4,
+           e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 template <int N>
 int run() {
     float *ss, *ts; long long* cyc;
@@ -156,6 +213,9 @@ int run() {
     return bad_ts != 0;
 }
 int main() {
+    long long* dd; cudaMalloc(&dd, 16);
+    run_rate<16, 4>(dd); run_rate<32, 4>(dd); run_rate<48, 4>(dd); run_rate<64, 4>(dd); run_rate<96, 4>(dd); run_rate<128, 2>(dd);
+    run_rate<32, 1>(dd); run_rate<96, 1>(dd);
     int bad = 0;
     bad += run<16>(); bad += run<32>(); bad += run<48>(); bad += run<64>(); bad += run<96>(); bad += run<128>();
     return bad ? 2 : 0;

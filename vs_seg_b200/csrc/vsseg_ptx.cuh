@@ -96,7 +96,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
-// same instruction, descriptors passed as their two 32-bit words (accumulate always on)
+// same instruction, descriptors passed as their two 32-bit words (accumulate always on).  No "memory" clobber: the
+// instruction touches no C++-visible memory and volatile asm statements keep their order among themselves (barrier
+// waits, fences and commits carry the clobbers); with the clobber the compiler re-loaded every kernel parameter the
+// issue loop uses (descriptor words, plane offsets) from the constant bank before each MMA - dependent LDCU chains
+// that held one issuing thread to one MMA per ~140 cycles
 __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                             uint32_t idesc) {
     asm volatile(
@@ -108,8 +112,7 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint
         "mov.b64 db, {%3, %4};\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
         "}\n" ::"r"(tmem_d),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
-        : "memory");
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc));
 }
 // A operand from tensor memory ("TS"): D[tmem] += A[tmem: 128 lanes x 8 columns = 128 x 16 bf16] * B[smem descriptor]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
@@ -121,8 +124,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "mov.b64 db, {%2, %3};\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
         "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc)
-        : "memory");
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc));
 }
 // shared memory (K-major SWIZZLE_NONE matrix descriptor: 128 rows x 32 bytes) -> tensor memory (128 lanes x 8 columns)
 __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint32_t s_lo, uint32_t s_hi) {
@@ -132,8 +134,7 @@ __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint32_t s_lo, 
         "mov.b64 ds, {%1, %2};\n"
         "tcgen05.cp.cta_group::1.128x256b [%0], ds;\n"
         "}\n" ::"r"(taddr),
-        "r"(s_lo), "r"(s_hi)
-        : "memory");
+        "r"(s_lo), "r"(s_hi));
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

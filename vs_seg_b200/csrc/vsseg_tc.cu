@@ -920,7 +920,11 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     int best_slots = 1;
     bool best_ts = false;
     // TS mode: stride-1 convs without z taps on 128-long z lines (box mode, every A view is one whole z line)
-    static const int ts_env = getenv("VSSEG_TC_TS") ? atoi(getenv("VSSEG_TC_TS")) : 1;   // 0 off, 1 cost model, 2 forced where possible
+    // Measured (tools/ubench/mma_ts.cu, profiles/r02_*): a tcgen05.mma M=128 K=16 has an execution floor of ~45 cycles
+    // for N <= 90 in BOTH modes (SS: max(45, 32 + N/4); TS: max(45, N/2)), so moving A to tensor memory only pays for
+    // N >= 96, while the two A buffers cost TMEM row slots - on this network TS is 5-40 % slower on every layer.
+    // Kept as an experiment (default off): VSSEG_TC_TS = 0 off, 1 cost model, 2 forced where possible.
+    static const int ts_env = getenv("VSSEG_TC_TS") ? atoi(getenv("VSSEG_TC_TS")) : 0;
     const bool ts_ok = ts_env != 0 && !tr && !strided && !line && KZ == 1 && LY == 1;
     const int sms_ = sm_count();
     for (int ts = 0; ts <= (ts_ok ? 1 : 0); ++ts)
