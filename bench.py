@@ -147,30 +147,43 @@ def train_record(dev, world, steps=5):
         opt.step()
         return loss
 
+    from vs_seg_b200.training import GraphedTrainStep
+    graphed = GraphedTrainStep(net, crit, opt, red)
+
+    def measure(fn, n):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        l0 = vlib.launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            loss = fn()
+        e1.record()
+        host = (time.perf_counter() - t0) * 1e3 / n   # host time to ISSUE a step (no sync inside)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), host, (vlib.launches() - l0) // n, loss
+
     for _ in range(2):
         step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    l0 = vlib.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(steps):
-        loss = step()
-    e1.record()
-    host_ms = (time.perf_counter() - t0) * 1e3 / steps   # host time to ISSUE a step (no sync inside)
-    torch.cuda.synchronize(dev)
-    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    eager_ms, eager_host, eager_launches, _ = measure(step, 3)
+    graphed(x, y)   # capture (includes its own warm-up; the training state is restored around it)
+    graphed(x, y)
+    ms_v, host_ms, _, loss = measure(lambda: graphed(x, y), steps)
+    ms = torch.tensor([ms_v])
     rec = {"workload": "training step, batch 2 x 128^3 per GPU: native fwd + Dice_spvPA + native bwd"
                        + (f" + 1 NCCL all-reduce of the flat gradient over {world} ranks" if world > 1 else "")
-                       + " + fused Adam (BASELINE configs[2]" + ("/[4])" if world > 1 else ")"),
+                       + " + fused Adam (BASELINE configs[2]" + ("/[4])" if world > 1 else ")")
+                       + ", the whole step replayed as one CUDA graph (GraphedTrainStep, what VS_train.py runs)",
            "n_gpus": world, "batch_per_gpu": 2, "ms_per_step": ms.item(), "samples_per_s": 2 * world / (ms.item() * 1e-3),
-           "host_issue_ms_per_step": host_ms, "native_launches_per_step": (vlib.launches() - l0) // steps,
+           "host_issue_ms_per_step": host_ms,
+           "eager": {"ms_per_step": eager_ms, "host_issue_ms_per_step": eager_host, "native_launches_per_step": eager_launches},
            "loss": float(loss), "dropout": 0.1, "steps": steps}
-    del net, opt, red
+    del net, opt, red, graphed
     torch.cuda.empty_cache()
     return rec
 

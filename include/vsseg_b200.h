@@ -283,13 +283,16 @@ int vsseg_bn_finalize(const double* sums, int32_t C, int64_t count, const float*
                       float eps, float momentum, float* running_mean, float* running_var, float* stats,
                       void* stream);
 /* slope: DEVICE pointer to the PReLU parameter (act.weight, one element): read by the kernel, so a training step never
- * copies parameters to the host and can be captured in a CUDA graph */
+ * copies parameters to the host and can be captured in a CUDA graph.
+ * seed_base: optional DEVICE scalar added to `seed` (the per-layer salt) on the device: a captured graph draws fresh
+ * dropout masks on every replay once the host stores a new base value before launching it. */
 int vsseg_bn_act_fwd(const vsseg_act8* c, const vsseg_act8* y, const float* stats, const float* slope, float drop_p,
-                     uint64_t seed, const vsseg_act8* residual, void* stream);
+                     uint64_t seed, const uint64_t* seed_base, const vsseg_act8* residual, void* stream);
 int vsseg_bn_act_bwd_reduce(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const float* slope,
-                            float drop_p, uint64_t seed, double* sums, void* stream);
+                            float drop_p, uint64_t seed, const uint64_t* seed_base, double* sums, void* stream);
 int vsseg_bn_act_bwd_apply(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const double* sums,
-                           const float* slope, float drop_p, uint64_t seed, const vsseg_act8* dc, void* stream);
+                           const float* slope, float drop_p, uint64_t seed, const uint64_t* seed_base,
+                           const vsseg_act8* dc, void* stream);
 int vsseg_act_bwd(const vsseg_act8* y, const vsseg_act8* dy, float slope, const vsseg_act8* dc, void* stream);
 int vsseg_act8_add(const vsseg_act8* a, const vsseg_act8* b, const vsseg_act8* out, void* stream);
 int vsseg_conv3d_wgrad(const vsseg_act8* x, const vsseg_act8* dc, const vsseg_conv_geom* g, float* dw,
@@ -312,10 +315,12 @@ int vsseg_att_gate_bwd(const vsseg_act8* x, const vsseg_f32view* att, const vsse
  * once per batch over 178 tensors).  One launch over flat fp32 buffers of n elements (16-byte aligned):
  *   g = grad * grad_scale + weight_decay * param;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
  *   param -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)        (torch.optim.Adam, amsgrad off)
- * grad_scale = 1 / world_size folds the data-parallel gradient average into the step. */
+ * grad_scale = 1 / world_size folds the data-parallel gradient average into the step.
+ * step_dev / lr_dev (both or neither; DEVICE scalars): when given, the step count and learning rate are read on the
+ * device instead of `step` / `lr`, so a captured CUDA graph of the training step stays valid as they change. */
 int vsseg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
-                    void* stream);
+                    const int64_t* step_dev, const float* lr_dev, void* stream);
 
 /* Builds the weight image vsseg_conv3d_tc streams (layout above) from a torch-layout fp32 weight on the device:
  * w is [d0][d1][kx][ky][kz]; conv_t_layout = 0: Conv3d [Cout][Cin] / 1: ConvTranspose3d [Cin][Cout]; phases = 1: the

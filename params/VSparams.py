@@ -408,6 +408,12 @@ class VSparams:
         if self.world_size > 1:
             ddp.broadcast_module_state(model)
         reducer = ddp.GradReducer(model, optimizer)
+        # CUDA: the loop body below (zero_grad .. optimizer.step, reference VSparams.py:457-462) is captured once per batch
+        # shape in a CUDA graph and replayed - the eager step is host-bound (~420 launches); VSSEG_GRAPH_STEP=0 disables
+        graphed_step = None
+        if self.device.type == "cuda" and os.environ.get("VSSEG_GRAPH_STEP", "1") != "0" and hasattr(optimizer, "pre_replay"):
+            from vs_seg_b200.training import GraphedTrainStep
+            graphed_step = GraphedTrainStep(model, loss_function, optimizer, reducer)
         start = perf_counter()
         for epoch in range(num_epochs):
             logger.info("-" * 10)
@@ -422,12 +428,15 @@ class VSparams:
             for batch_data in train_loader:
                 step += 1
                 inputs, labels = batch_data["image"].to(self.device), batch_data["label"].to(self.device)
-                optimizer.zero_grad()
-                outputs = model(inputs)
-                loss = loss_function(outputs, labels)
-                loss.backward()
-                reducer.reduce()
-                optimizer.step()
+                if graphed_step is not None:
+                    loss = graphed_step(inputs, labels)
+                else:
+                    optimizer.zero_grad()
+                    outputs = model(inputs)
+                    loss = loss_function(outputs, labels)
+                    loss.backward()
+                    reducer.reduce()
+                    optimizer.step()
                 # the loss stays on the device (no host sync per step); it is read once per epoch / log line
                 epoch_loss = epoch_loss + loss.detach()
                 if epoch == 0:

@@ -439,6 +439,44 @@ def test_unet_train_step_matches_torch_autograd(attention, shape):
         assert (bn[name].cpu().float() - b.float()).abs().max().item() < 1e-4 * max(1.0, b.float().abs().max().item()), name
 
 
+def test_unet_train_gradients_vs_fp64_bound_by_storage_precision():
+    """Why the gradient tolerance above is loose, as a test: the native gradients AND torch's own fp32 gradients are
+    compared with an fp64 autograd run of the same step.  The train-mode BatchNorm chain amplifies rounding (torch fp32
+    itself is off by up to 1.6e-2 of a tensor's largest gradient entry); the native path stores activations and
+    gradients as split-bf16 (16 mantissa bits against fp32's 24, i.e. 2^8 coarser), so its error must stay within
+    2^7 x max(fp32's own error, 1e-4 of the tensor's largest entry) - measured: median ratio 20, see
+    profiles/r02_train_grad_vs_fp64.json - and the projection on the fp64 gradient within 3 %."""
+    import copy
+    from params.losses.dice_spvPA import Dice_spvPA
+    ref32, nat = _train_pair(True)
+    ref64 = copy.deepcopy(ref32).double()
+    shape = (2, 1, 64, 64, 16)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g)
+    y = (torch.rand((shape[0], 1) + shape[2:], generator=g) > 0.7).float()
+    crit = Dice_spvPA(to_onehot_y=True, softmax=True)
+    crit(ref64(x.double()), y.double()).backward()
+    crit(ref32(x), y).backward()
+    crit(nat(x.to(_dev())), y.to(_dev())).backward()
+    p64, p32, pn = dict(ref64.named_parameters()), dict(ref32.named_parameters()), dict(nat.named_parameters())
+    gmax_all = max(p.grad.abs().max().item() for p in p64.values())
+    ratios = []
+    for name, p in p64.items():
+        g64 = p.grad
+        gmax = g64.abs().max().item()
+        if gmax < 1e-9:
+            continue
+        e32 = (p32[name].grad.double() - g64).abs().max().item() / gmax
+        en = (pn[name].grad.cpu().double() - g64).abs().max().item() / gmax
+        ratios.append(en / max(e32, 1e-4))
+        assert en <= 128 * max(e32, 1e-4) + 1e-4 * gmax_all / gmax, (name, en, e32)
+        if gmax > 1e-3 * gmax_all and g64.numel() > 1:
+            proj = ((pn[name].grad.cpu().double() * g64).sum() / (g64 * g64).sum()).item()
+            assert abs(proj - 1.0) < 3e-2, (name, proj)
+    ratios.sort()
+    assert ratios[len(ratios) // 2] < 64, ratios[len(ratios) // 2]   # median ratio (measured ~20)
+
+
 @pytest.mark.parametrize("B,cin,cout,dims,k", [
     (1, 16, 16, (4, 6, 128), (3, 3, 1)), (2, 32, 48, (3, 4, 128), (3, 3, 3)), (1, 96, 48, (2, 3, 128), (3, 3, 3)),
     (1, 64, 32, (4, 4, 256), (3, 3, 1)), (1, 16, 32, (4, 4, 128), (1, 1, 1)), (1, 48, 40, (3, 3, 128), (3, 3, 3)),

@@ -344,6 +344,50 @@ def test_ts_mode_conv_parity_in_a_subprocess():
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
+def test_graphed_train_step_matches_eager_steps():
+    """The training step replayed as one CUDA graph (GraphedTrainStep) == the eager native step: same losses and the same
+    parameters / BatchNorm statistics / Adam moments after several steps on changing batches (dropout 0; the weight
+    gradients use fp32 atomics, so equality is to rounding), a learning-rate change in between is honoured, the capture's
+    warm-up steps leave no trace, and tensor versions are bumped for the cached eval plans."""
+    import copy
+    from params.losses.dice_spvPA import Dice_spvPA
+    from params.networks.nets.unet2d5_spvPA import UNet2d5_spvPA
+    from vs_seg_b200.optim import FusedAdam
+    from vs_seg_b200.training import GraphedTrainStep
+    torch.manual_seed(0)
+    a = UNet2d5_spvPA(dimensions=3, in_channels=1, out_channels=2, channels=unet_oracle.CHANNELS, strides=unet_oracle.STRIDES,
+                      kernel_sizes=unet_oracle.KERNEL_SIZES, sample_kernel_sizes=unet_oracle.SAMPLE_KERNEL_SIZES,
+                      num_res_units=2, norm="BATCH", dropout=0.0).to(_dev()).train()
+    b = copy.deepcopy(a)
+    oa, ob = FusedAdam(a.parameters(), lr=1e-3, weight_decay=1e-7), FusedAdam(b.parameters(), lr=1e-3, weight_decay=1e-7)
+    crit = Dice_spvPA(to_onehot_y=True, softmax=True)
+    graphed = GraphedTrainStep(b, crit, ob)
+    g = torch.Generator().manual_seed(9)
+    v0 = next(b.parameters())._version
+    for i in range(4):
+        x = torch.randn((2, 1, 64, 64, 16), generator=g).to(_dev())
+        y = (torch.rand((2, 1, 64, 64, 16), generator=g) > 0.7).float().to(_dev())
+        if i == 2:
+            for opt in (oa, ob):
+                opt.param_groups[0]["lr"] = 2.5e-4
+        oa.zero_grad()
+        la = crit(a(x), y)
+        la.backward()
+        oa.step()
+        lb = graphed(x, y)
+        assert abs(la.item() - lb.item()) < 1e-4 * max(1.0, abs(la.item())), (i, la.item(), lb.item())
+    assert oa.param_groups[0]["step"] == ob.param_groups[0]["step"] == 4
+    assert next(b.parameters())._version > v0
+    # Adam normalises the update to ~lr per step whatever the gradient's size, so an element whose gradient is at the
+    # rounding level of the atomics may move differently: compare the bulk tightly and bound the stragglers by the
+    # total step length (4 steps x lr)
+    d = torch.cat([(p1 - p2).detach().abs().reshape(-1) for p1, p2 in zip(a.parameters(), b.parameters())])
+    assert (d > 1e-4).float().mean().item() < 0.01, (d > 1e-4).float().mean().item()
+    assert d.max().item() < 8e-3, d.max().item()
+    for (n1, b1), (_, b2) in zip(a.named_buffers(), b.named_buffers()):
+        assert (b1.float() - b2.float()).abs().max().item() < 1e-4 * max(1.0, b1.float().abs().max().item()), n1
+
+
 # ---- two ranks over NCCL ----------------------------------------------------------------------------------------
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
 def test_two_rank_nccl_sharded_inference_equals_one_gpu(tmp_path):

@@ -9,7 +9,22 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, 
                                                         float4* __restrict__ v, int64_t n4, float* __restrict__ pt,
                                                         const float* __restrict__ gt, float* __restrict__ mt, float* __restrict__ vt,
                                                         int ntail, float beta1, float beta2, float eps, float wd, float step_size,
-                                                        float inv_bc2_sqrt, float grad_scale) {
+                                                        float inv_bc2_sqrt, float grad_scale, const long long* __restrict__ step_dev,
+                                                        const float* __restrict__ lr_dev) {
+    if (step_dev) {
+        // graph-capturable form: the step count and the learning rate live in device memory (a captured launch must not
+        // bake them in); bias corrections in double like torch.optim.Adam, once per block
+        __shared__ float sh[2];
+        if (threadIdx.x == 0) {
+            const double t = (double)*step_dev;
+            const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+            sh[0] = (float)((double)*lr_dev / bc1);
+            sh[1] = (float)(1.0 / sqrt(bc2));
+        }
+        __syncthreads();
+        step_size = sh[0];
+        inv_bc2_sqrt = sh[1];
+    }
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
         gg = fmaf(wd, pp, gg * grad_scale);                 // grad (averaged over ranks) + weight_decay * param
         mm = fmaf(beta1, mm, (1.f - beta1) * gg);
@@ -36,8 +51,11 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, 
 using namespace vsseg;
 
 extern "C" int vsseg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                               float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
-    VSSEG_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+                               float beta2, float eps, float weight_decay, int64_t step, float grad_scale, const int64_t* step_dev,
+                               const float* lr_dev, void* stream) {
+    VSSEG_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && (step >= 1 || step_dev), "adam_step: bad arguments");
+    VSSEG_REQUIRE(!step_dev == !lr_dev, "adam_step: step_dev and lr_dev go together");
+    if (step_dev) step = 1;   // unused by the kernel
     VSSEG_REQUIRE(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0,
                   "adam_step: buffers must be 16-byte aligned");
     // bias corrections in double on the host, exactly as torch.optim.Adam computes them
@@ -51,7 +69,8 @@ extern "C" int vsseg_adam_step(float* param, const float* grad, float* exp_avg, 
     if (blocks < 1) blocks = 1;
     adam_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq, n4, param + n4 * 4, grad + n4 * 4, exp_avg + n4 * 4,
-        exp_avg_sq + n4 * 4, ntail, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale);
+        exp_avg_sq + n4 * 4, ntail, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, grad_scale, (const long long*)step_dev,
+        lr_dev);
     return check_launch("adam_step");
 }
 

@@ -126,8 +126,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
 
 // ---- forward: y = PReLU(dropout(c*scale + shift)) [+ residual] ------------------------------------------
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(vsseg_act8 c, vsseg_act8 y, const float* __restrict__ stats, const float* __restrict__ slope_p,
-                                                         float drop_p, uint64_t seed, vsseg_act8 res, int has_res) {
+                                                         float drop_p, uint64_t seed, const uint64_t* __restrict__ seed_base, vsseg_act8 res,
+                                                         int has_res) {
     const float slope = __ldg(slope_p);   // the PReLU parameter is read on the device: no host copy, graph-capturable
+    if (seed_base) seed += __ldg(reinterpret_cast<const unsigned long long*>(seed_base));
     const G8 it(c);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < it.total; i += (int64_t)gridDim.x * blockDim.x) {
         int b, cg;
@@ -151,8 +153,9 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(vsseg_act8 c, vsseg_act
 // ---- backward reductions: sums[0][C] = sum du, sums[1][C] = sum du*xhat, sums[2C] = d(slope) -------------
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(vsseg_act8 c, vsseg_act8 dy, const float* __restrict__ stats,
                                                                 const float* __restrict__ slope_p, float drop_p, uint64_t seed,
-                                                                double* __restrict__ sums) {
+                                                                const uint64_t* __restrict__ seed_base, double* __restrict__ sums) {
     const float slope = __ldg(slope_p);
+    if (seed_base) seed += __ldg(reinterpret_cast<const unsigned long long*>(seed_base));
     const int cg = blockIdx.y;
     const int64_t nvox = (int64_t)c.X * c.Y * c.Z, total = nvox * c.B;
     float s[8], q[8], da = 0.f;
@@ -212,8 +215,9 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(vsseg_act8 c, vs
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(vsseg_act8 c, vsseg_act8 dy, const float* __restrict__ stats,
                                                                const double* __restrict__ sums, double inv_count,
                                                                const float* __restrict__ slope_p, float drop_p, uint64_t seed,
-                                                               vsseg_act8 dc) {
+                                                               const uint64_t* __restrict__ seed_base, vsseg_act8 dc) {
     const float slope = __ldg(slope_p);
+    if (seed_base) seed += __ldg(reinterpret_cast<const unsigned long long*>(seed_base));
     const G8 it(c);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < it.total; i += (int64_t)gridDim.x * blockDim.x) {
         int b, cg;
@@ -696,32 +700,33 @@ int vsseg_bn_finalize(const double* sums, int32_t C, int64_t count, const float*
 }
 
 int vsseg_bn_act_fwd(const vsseg_act8* c, const vsseg_act8* y, const float* stats, const float* slope, float drop_p,
-                     uint64_t seed, const vsseg_act8* residual, void* stream) {
+                     uint64_t seed, const uint64_t* seed_base, const vsseg_act8* residual, void* stream) {
     VSSEG_REQUIRE(a8ok(c) && a8ok(y) && same_shape(c, y) && stats && slope, "bn_act_fwd: bad arguments");
     VSSEG_REQUIRE(!residual || (a8ok(residual) && same_shape(residual, c)), "bn_act_fwd: residual shape mismatch");
     VSSEG_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "bn_act_fwd: dropout probability must be in [0,1)");
     const int64_t total = (int64_t)c->B * (c->C / 8) * c->X * c->Y * c->Z;
-    bn_act_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(*c, *y, stats, slope, drop_p, seed,
+    bn_act_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(*c, *y, stats, slope, drop_p, seed, seed_base,
                                                                             residual ? *residual : *c, residual ? 1 : 0);
     return check_launch("bn_act_fwd");
 }
 
 int vsseg_bn_act_bwd_reduce(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const float* slope, float drop_p,
-                            uint64_t seed, double* sums, void* stream) {
+                            uint64_t seed, const uint64_t* seed_base, double* sums, void* stream) {
     VSSEG_REQUIRE(a8ok(c) && a8ok(dy) && same_shape(c, dy) && stats && sums && slope, "bn_act_bwd_reduce: bad arguments");
     const int64_t total = (int64_t)c->B * c->X * c->Y * c->Z;
     dim3 grid(ew_grid(total, 256 * 8), (unsigned)(c->C / 8));
-    bn_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*c, *dy, stats, slope, drop_p, seed, sums);
+    bn_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*c, *dy, stats, slope, drop_p, seed, seed_base, sums);
     return check_launch("bn_act_bwd_reduce");
 }
 
 int vsseg_bn_act_bwd_apply(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const double* sums,
-                           const float* slope, float drop_p, uint64_t seed, const vsseg_act8* dc, void* stream) {
+                           const float* slope, float drop_p, uint64_t seed, const uint64_t* seed_base, const vsseg_act8* dc,
+                           void* stream) {
     VSSEG_REQUIRE(a8ok(c) && a8ok(dy) && a8ok(dc) && same_shape(c, dy) && same_shape(c, dc) && stats && sums && slope,
                   "bn_act_bwd_apply: bad arguments");
     const int64_t count = (int64_t)c->B * c->X * c->Y * c->Z;
     bn_act_bwd_apply_kernel<<<ew_grid(count * (c->C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-        *c, *dy, stats, sums, 1.0 / (double)count, slope, drop_p, seed, *dc);
+        *c, *dy, stats, sums, 1.0 / (double)count, slope, drop_p, seed, seed_base, *dc);
     return check_launch("bn_act_bwd_apply");
 }
 

@@ -84,12 +84,12 @@ _SIGNATURES = {
     "vsseg_bn_stats": (C.c_int, [_P(Act8), C.c_void_p, C.c_void_p]),
     "vsseg_bn_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "vsseg_bn_act_fwd": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, _P(Act8),
+    "vsseg_bn_act_fwd": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p, _P(Act8),
                                    C.c_void_p]),
     "vsseg_bn_act_bwd_reduce": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p,
-                                          C.c_void_p]),
+                                          C.c_void_p, C.c_void_p]),
     "vsseg_bn_act_bwd_apply": (C.c_int, [_P(Act8), _P(Act8), C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64,
-                                         _P(Act8), C.c_void_p]),
+                                         C.c_void_p, _P(Act8), C.c_void_p]),
     "vsseg_act_bwd": (C.c_int, [_P(Act8), _P(Act8), C.c_float, _P(Act8), C.c_void_p]),
     "vsseg_act8_add": (C.c_int, [_P(Act8), _P(Act8), _P(Act8), C.c_void_p]),
     "vsseg_conv3d_wgrad": (C.c_int, [_P(Act8), _P(Act8), _P(ConvGeom), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -100,7 +100,7 @@ _SIGNATURES = {
                                              _P(Act8), C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsseg_att_gate_bwd": (C.c_int, [_P(Act8), _P(F32View), _P(Act8), _P(Act8), _P(F32View), C.c_int32, C.c_void_p]),
     "vsseg_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
-                                  C.c_float, C.c_float, C.c_int64, C.c_float, C.c_void_p]),
+                                  C.c_float, C.c_float, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsseg_pack_conv_weight_tc": (C.c_int, [C.c_void_p] + [C.c_int32] * 11 + [C.c_void_p, C.c_void_p]),
     "vsseg_sw_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -57,10 +57,10 @@ class _DiceSpvPA(torch.autograd.Function):
         # rows: [att level 0 (finest) .. L-1] each B rows, then logits B*2 rows
         nrows = L * B + 2 * B
         sums = torch.zeros((nrows, 3), dtype=torch.float64, device=dev)
-        scale = torch.empty(nrows, dtype=torch.float32)
-        scale[:L * B] = 1.0 / (max(L, 1) * B)
-        scale[L * B:] = 1.0 / (2 * B)
-        scale = scale.to(dev, non_blocking=True)
+        # built on the device (a host->device copy of a pageable tensor cannot be captured in a CUDA graph)
+        scale = torch.full((nrows,), 1.0 / (2 * B), dtype=torch.float32, device=dev)
+        if L:
+            scale[:L * B] = 1.0 / (L * B)
         for level in range(L):
             a = atts[L - level - 1]
             _lib.check(lib.vsseg_dice_sums(a.data_ptr(), labels[level].data_ptr(), B, 1, a[0].numel(), -1.0,

@@ -51,7 +51,8 @@ class FusedAdam(torch.optim.Optimizer):
                 p.data = view                                   # the module's parameter now lives in the flat buffer
                 p.grad = flat_g[off:off + p.numel()].view(p.shape)   # autograd accumulates in place
                 off += sz
-        return dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), n=n, params=ps)
+        return dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), n=n, params=ps,
+                    step_dev=torch.zeros(1, dtype=torch.int64, device=dev), lr_dev=torch.zeros(1, dtype=torch.float32, device=dev))
 
     # ---- torch.optim.Optimizer interface ------------------------------------------------------
     def zero_grad(self, set_to_none: bool = True):
@@ -103,6 +104,22 @@ class FusedAdam(torch.optim.Optimizer):
         """The flat gradient buffers (one per CUDA group): what a data-parallel run all-reduces."""
         return [fl["g"] for fl in self._flat if fl is not None]
 
+    def pre_replay(self):
+        """Host side of a graph-captured step (vs_seg_b200.training.GraphedTrainStep): advance the step counters and store
+        step count and learning rate in the device scalars the captured Adam launch reads."""
+        for group, fl in zip(self.param_groups, self._flat):
+            group["step"] += 1
+            if fl is not None:
+                fl["step_dev"].fill_(int(group["step"]))
+                fl["lr_dev"].fill_(float(group["lr"]))
+
+    def post_replay(self):
+        """The captured launch wrote the parameters through raw pointers: bump the tensor versions (cached eval plans
+        key on them)."""
+        for fl in self._flat:
+            if fl is not None:
+                torch._C._increment_version(fl["params"])
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -110,8 +127,10 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = None
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         for group, fl, opt in zip(self.param_groups, self._flat, self._cpu_opt):
-            group["step"] += 1
+            if not capturing:   # a captured step is counted by pre_replay() before every replay
+                group["step"] += 1
             if fl is None:
                 for g2 in opt.param_groups:   # lr halving is done through OUR param_groups
                     g2["lr"], g2["weight_decay"] = group["lr"], group["weight_decay"]
@@ -127,7 +146,9 @@ class FusedAdam(torch.optim.Optimizer):
             s = torch.cuda.current_stream(fl["p"].device).cuda_stream
             _lib.check(lib.vsseg_adam_step(fl["p"].data_ptr(), fl["g"].data_ptr(), fl["m"].data_ptr(), fl["v"].data_ptr(),
                                            fl["n"], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                           float(group["weight_decay"]), int(group["step"]), float(self.grad_scale), s),
+                                           float(group["weight_decay"]), max(int(group["step"]), 1), float(self.grad_scale),
+                                           fl["step_dev"].data_ptr() if capturing else None,
+                                           fl["lr_dev"].data_ptr() if capturing else None, s),
                        "adam_step")
             _lib.count_launch()
             # the kernel wrote through raw pointers: tell torch (cached eval plans key on tensor versions)

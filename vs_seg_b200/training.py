@@ -33,6 +33,19 @@ def _lib_tc_wgrad():
     return os.environ.get("VSSEG_TC_WGRAD", "1") != "0"
 
 
+_SEED_BASE: dict = {}
+
+
+def dropout_seed_base(device) -> torch.Tensor:
+    """Per-device int64 scalar the BN/activation kernels add to their per-layer dropout salt.  It is rewritten before every
+    step (eagerly by UNetTrainStep, or by GraphedTrainStep before a replay), so captured launches draw fresh masks."""
+    key = str(torch.device(device))
+    t = _SEED_BASE.get(key)
+    if t is None:
+        t = _SEED_BASE[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return t
+
+
 class _GradBuf:
     """Gradient of an activation tensor: first writer stores, later writers accumulate."""
 
@@ -56,7 +69,12 @@ class UNetTrainStep:
         self.p = dict(model.named_parameters())
         self.bufs = dict(model.named_buffers())
         self.drop_p = float(model.dropout or 0.0)
-        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        # dropout masks = hash(per-layer salt + device-side base, element): the base is redrawn every step; while a CUDA
+        # graph is being captured the launch only records the pointer (GraphedTrainStep stores a new base per replay)
+        self.seed = 0
+        self.seed_base = dropout_seed_base(self.dev)
+        if not torch.cuda.is_current_stream_capturing():
+            self.seed_base.fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
         self.layer_id = 0
 
     # ---- small helpers --------------------------------------------------------------------------------
@@ -215,12 +233,13 @@ class UNetTrainStep:
         self.layer_id += 1
         seed = (self.seed + 0x1000003 * self.layer_id) & (2 ** 63 - 1)
         res_p = C.byref(residual) if residual is not None else None
-        self._chk(lib.vsseg_bn_act_fwd(C.byref(c), C.byref(dst), stats.data_ptr(), slope, self.drop_p, seed, res_p, s), "bn_act_fwd")
+        sb = self.seed_base.data_ptr()
+        self._chk(lib.vsseg_bn_act_fwd(C.byref(c), C.byref(dst), stats.data_ptr(), slope, self.drop_p, seed, sb, res_p, s), "bn_act_fwd")
         self.keep += [sums, stats, c, dst, src, residual]
 
         def backward(dy):
             sums2 = torch.zeros(2 * Cc + 1, dtype=torch.float64, device=self.dev)
-            self._chk(lib.vsseg_bn_act_bwd_reduce(C.byref(c), C.byref(dy), stats.data_ptr(), slope, self.drop_p, seed,
+            self._chk(lib.vsseg_bn_act_bwd_reduce(C.byref(c), C.byref(dy), stats.data_ptr(), slope, self.drop_p, seed, sb,
                                                   sums2.data_ptr(), s), "bn_act_bwd_reduce")
             self._addgrad(prefix + "norm.bias", sums2[:Cc].float())
             self._addgrad(prefix + "norm.weight", sums2[Cc:2 * Cc].float())
@@ -228,7 +247,7 @@ class UNetTrainStep:
             dcb = Act8Buffer(dst.B, Cc, dst.X, dst.Y, dst.Z, self.dev)
             dc = dcb.view()
             self._chk(lib.vsseg_bn_act_bwd_apply(C.byref(c), C.byref(dy), stats.data_ptr(), sums2.data_ptr(), slope, self.drop_p,
-                                                 seed, C.byref(dc), s), "bn_act_bwd_apply")
+                                                 seed, sb, C.byref(dc), s), "bn_act_bwd_apply")
             if cin1 is not None:
                 taps = k[0] * k[1] * k[2]
                 dw = torch.zeros((taps, Cc), device=self.dev)
@@ -625,3 +644,87 @@ def block_train_forward(module, x):
                                   "channels % 8 == 0 (ResidualUnit: stride 1, 1x1x1 shortcut)")
     named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
     return _BlockTrainFn.apply(module, x.float(), kind, tuple(n for n, _ in named), *[p for _, p in named])
+
+
+# ---- the whole training step as one CUDA graph -----------------------------------------------------------------------
+class GraphedTrainStep:
+    """``loss = step(inputs, labels)`` = the reference's inner loop body (VSparams.py:457-462: zero_grad, forward, loss,
+    backward, optimizer.step) captured ONCE per input shape in a CUDA graph and replayed.
+
+    The eager step issues ~420 native launches plus the Python tape around them (~40 ms of host time at best, several
+    times that when the host cores are shared), which made the step host-bound and the data-parallel step scale badly.
+    A replay costs the host four calls: copy the batch into the graph's static input tensors, store a fresh dropout seed
+    base and the Adam step count / learning rate in device scalars (the captured kernels read them there), launch.
+    BatchNorm running statistics, the flat Adam moments and, under torchrun, the NCCL all-reduce of the flat gradient are
+    all part of the graph.  Parameters must belong to a ``FusedAdam`` on CUDA.
+    """
+
+    def __init__(self, model, loss_function, optimizer, reducer=None, warmup=2):
+        self.model, self.loss_function, self.optimizer, self.reducer = model, loss_function, optimizer, reducer
+        self.warmup = int(warmup)
+        self._graphs = {}
+        if not hasattr(optimizer, "pre_replay"):
+            raise TypeError("GraphedTrainStep needs a vs_seg_b200.optim.FusedAdam")
+
+    def _eager(self, x, y):
+        self.optimizer.zero_grad()
+        loss = self.loss_function(self.model(x), y)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.reduce()
+        self.optimizer.step()
+        return loss.detach()
+
+    def _snapshot(self):
+        fl = [f for f in self.optimizer._flat if f is not None]
+        return ([(f, f["p"].clone(), f["m"].clone(), f["v"].clone()) for f in fl],
+                [(b, b.clone()) for b in self.model.buffers()], [g["step"] for g in self.optimizer.param_groups])
+
+    def _restore(self, snap):
+        flat, bufs, steps = snap
+        with torch.no_grad():
+            for f, p, m, v in flat:
+                f["p"].copy_(p)
+                f["m"].copy_(m)
+                f["v"].copy_(v)
+            for b, c in bufs:
+                b.copy_(c)
+        for g, st in zip(self.optimizer.param_groups, steps):
+            g["step"] = st
+
+    def _capture(self, inputs, labels):
+        dev = inputs.device
+        sx, sy = inputs.detach().clone(), labels.detach().clone()
+        # warm-up passes on a side stream (lazy initialisation, allocator pools, function attributes must not happen inside
+        # the capture); they are real steps on this batch, so the training state is put back afterwards
+        snap = self._snapshot()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self._eager(sx, sy)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._restore(snap)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            loss = self._eager(sx, sy)
+        return {"graph": graph, "x": sx, "y": sy, "loss": loss}
+
+    def __call__(self, inputs, labels):
+        if not inputs.is_cuda:
+            raise _lib.NativeLibraryError("GraphedTrainStep runs on CUDA tensors only")
+        key = (tuple(inputs.shape), inputs.dtype, tuple(labels.shape), labels.dtype, str(inputs.device))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 2:   # every graph keeps the activations of a whole step alive
+                self._graphs.clear()
+            g = self._graphs[key] = self._capture(inputs, labels)
+        g["x"].copy_(inputs, non_blocking=True)
+        g["y"].copy_(labels, non_blocking=True)
+        dropout_seed_base(inputs.device).fill_(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        self.optimizer.pre_replay()
+        g["graph"].replay()
+        self.optimizer.post_replay()
+        _lib.count_launch()
+        return g["loss"]
