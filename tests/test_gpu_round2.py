@@ -151,6 +151,29 @@ def test_captured_graph_equals_direct_launches_and_follows_the_volume(monkeypatc
     assert (outs["1"][1] - ref).abs().max().item() < 1e-3
 
 
+def test_two_stream_window_groups_match_one_stream(monkeypatch):
+    """VSSEG_SW_STREAMS=2 (two window groups with disjoint destinations run concurrently on two streams, joined per
+    phase) == the one-stream schedule up to the fp32 order of overlapping windows of different phases."""
+    from vs_seg_b200 import sliding_window as sw
+    sd = unet_oracle.seeded_state_dict(4)
+    net = _native_net(sd)
+    roi = (64, 64, 16)
+    x = torch.randn((1, 1, 160, 64, 16), generator=torch.Generator().manual_seed(23)).to(_dev())   # 4 x windows
+    monkeypatch.setenv("VSSEG_SW_GROUP", "1")
+    outs = []
+    for streams in ("1", "2"):
+        monkeypatch.setenv("VSSEG_SW_STREAMS", streams)
+        sw._PROGRAMS.clear()
+        with torch.no_grad():
+            outs.append([sw.sliding_window_inference(x, roi, 1, net, mode="gaussian").clone() for _ in range(2)])
+        prog = next(iter(sw._PROGRAMS.values()))
+        assert prog.streams == int(streams)
+        if streams == "2":
+            assert any(len(ph) == 2 for ph in prog.phases)
+    assert torch.equal(outs[1][0], outs[1][1])
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5
+
+
 def test_sliding_window_rejects_train_mode():
     from vs_seg_b200.sliding_window import sliding_window_inference
     net = _native_net(unet_oracle.seeded_state_dict(4)).train()

@@ -156,19 +156,32 @@ class _Program:
         self.cell = torch.zeros(2, dtype=torch.int64, device=dev)   # [input base, accumulator base]
         self.imap = imap
         cell = self.cell.data_ptr()
+        groups = [jobs[g0:g0 + group] for g0 in range(0, len(jobs), group)]
+        # VSSEG_SW_STREAMS=2: two window groups whose destination regions are disjoint run concurrently on two streams
+        # (two plans with their own activation buffers; the latency-bound coarse levels of one group overlap the
+        # bandwidth-bound fine levels of the other).  Phases are joined before the next pair starts, so overlapping
+        # windows are still blended in a fixed order (no atomics needed).
+        self.streams = 2 if (os.environ.get("VSSEG_SW_STREAMS", "1") == "2" and not self.peer and len(groups) >= 2) else 1
+        self.side = torch.cuda.Stream(dev) if self.streams == 2 else None
+        phases = self._pair_groups(groups, roi_size) if self.streams == 2 else [[i] for i in range(len(groups))]
         self.calls = []   # (plan, srcs, dsts)
-        for g0 in range(0, len(jobs), group):
-            grp = jobs[g0:g0 + group]
-            srcs = [self._src_view(inputs, b, s, roi_size, cell) for b, s in grp]
-            if self.peer:
-                dsts = [self._acc_view(self.acc_shape, b, s, roi_size, cell + 8) for b, s in grp]
-            else:
-                dsts = [f32view(self.acc[b:b + 1], s, roi_size) for b, s in grp]
-            if len(grp) == 1:
-                self.calls.append((model.eval_plan(roi_size, batch=1, device=dev), srcs[0], dsts[0]))
-            else:
-                plan = model.eval_plan(roi_size, batch=len(grp), device=dev, window_levels=levels)
-                self.calls.append((plan, srcs, dsts))
+        self.phases = []  # lists of 1 or 2 indices into self.calls
+        for ph in phases:
+            idx = []
+            for slot, gi in enumerate(ph):
+                grp = groups[gi]
+                srcs = [self._src_view(inputs, b, s, roi_size, cell) for b, s in grp]
+                if self.peer:
+                    dsts = [self._acc_view(self.acc_shape, b, s, roi_size, cell + 8) for b, s in grp]
+                else:
+                    dsts = [f32view(self.acc[b:b + 1], s, roi_size) for b, s in grp]
+                if len(grp) == 1:
+                    call = (model.eval_plan(roi_size, batch=1, device=dev, slot=slot), srcs[0], dsts[0])
+                else:
+                    call = (model.eval_plan(roi_size, batch=len(grp), device=dev, window_levels=levels, slot=slot), srcs, dsts)
+                idx.append(len(self.calls))
+                self.calls.append(call)
+            self.phases.append(idx)
         self.launches = sum(len(p.steps) for p, _, _ in self.calls)
         self.graph = None
         if os.environ.get("VSSEG_SW_GRAPH", "1") != "0" and self.calls:
@@ -202,12 +215,51 @@ class _Program:
         off = 4 * (b * Cc * sc + start[0] * sx + start[1] * sy + start[2] * sz)
         return _lib.F32View(off, Cc * sc, sc, sx, sy, sz, 1, Cc, roi_size[0], roi_size[1], roi_size[2], 0, cell)
 
+    @staticmethod
+    def _pair_groups(groups, roi_size):
+        """Phases of one or two groups; the two groups of a phase blend into disjoint regions of the accumulator."""
+        def box(grp):
+            bs = [b for b, _ in grp]
+            lo = [min(s[d] for _, s in grp) for d in range(3)]
+            hi = [max(s[d] for _, s in grp) + roi_size[d] for d in range(3)]
+            return min(bs), max(bs), lo, hi
+
+        def disjoint(p, q):
+            if p[1] < q[0] or q[1] < p[0]:
+                return True
+            return any(p[3][d] <= q[2][d] or q[3][d] <= p[2][d] for d in range(3))
+
+        boxes = [box(g) for g in groups]
+        left, phases = list(range(len(groups))), []
+        while left:
+            i = left.pop(0)
+            j = next((k for k in left if disjoint(boxes[i], boxes[k])), None)
+            if j is None:
+                phases.append([i])
+            else:
+                left.remove(j)
+                phases.append([i, j])
+        return phases
+
     def _issue(self):
         if not self.peer:
             self.acc.zero_()
         wptr = self.imap.data_ptr()
-        for plan, srcs, dsts in self.calls:
+        cur = torch.cuda.current_stream(self.cell.device)
+        for ph in self.phases:
+            if len(ph) == 2:   # fork: the second group of the phase runs on the side stream
+                fork = torch.cuda.Event()
+                fork.record(cur)
+                self.side.wait_event(fork)
+                with torch.cuda.stream(self.side):
+                    plan, srcs, dsts = self.calls[ph[1]]
+                    plan.run(srcs, dsts, wptr, count=False, atomic=self.peer)
+                    join = torch.cuda.Event()
+                    join.record(self.side)
+            plan, srcs, dsts = self.calls[ph[0]]
             plan.run(srcs, dsts, wptr, count=False, atomic=self.peer)
+            if len(ph) == 2:
+                cur.wait_event(join)
 
     def run(self, inputs, acc_ptr=None):
         """Accumulate every window of `inputs` (same layout as the volume the program was built for).
@@ -232,7 +284,7 @@ def _program(model, inputs, roi_size, jobs, imap, image_size, extra, peer=False)
     """Cached _Program for (model weights, volume layout, geometry, shard)."""
     key = (id(model), model._weights_version(), tuple(inputs.shape), tuple(inputs.stride()), str(inputs.device),
            tuple(roi_size), extra, os.environ.get("VSSEG_SW_GROUP", "8"), os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"),
-           os.environ.get("VSSEG_SW_GRAPH", "1"), bool(peer))
+           os.environ.get("VSSEG_SW_GRAPH", "1"), os.environ.get("VSSEG_SW_STREAMS", "1"), bool(peer))
     prog = _PROGRAMS.get(key)
     if prog is None:
         if len(_PROGRAMS) >= 3:   # each program owns an accumulator volume and a captured graph
