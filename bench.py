@@ -145,7 +145,7 @@ def train_record(dev, world, steps=5):
         loss.backward()
         red.reduce()
         opt.step()
-        return loss
+        return loss.detach()
 
     from vs_seg_b200.training import GraphedTrainStep
     graphed = GraphedTrainStep(net, crit, opt, red)

@@ -177,6 +177,7 @@ def test_sliding_window_ragged_groups(monkeypatch):
     net = _native_net(unet_oracle.seeded_state_dict(4))
     x = torch.randn((1, 1, 96, 80, 24), generator=torch.Generator().manual_seed(21)).to(_dev())
     outs = []
+    monkeypatch.setenv("VSSEG_SW_STREAMS", "1")   # one stream: windows are blended in MONAI's order whatever the grouping
     for group in ("1", "3", "4"):
         monkeypatch.setenv("VSSEG_SW_GROUP", group)
         with torch.no_grad():

@@ -386,6 +386,13 @@ def test_graphed_train_step_matches_eager_steps():
     crit = Dice_spvPA(to_onehot_y=True, softmax=True)
     graphed = GraphedTrainStep(b, crit, ob)
     g = torch.Generator().manual_seed(9)
+    # one eager step on both models first: the graphed step must cope with autograd state left behind by eager steps
+    x0 = torch.randn((2, 1, 64, 64, 16), generator=g).to(_dev())
+    y0 = (torch.rand((2, 1, 64, 64, 16), generator=g) > 0.7).float().to(_dev())
+    for m, opt in ((a, oa), (b, ob)):
+        opt.zero_grad()
+        crit(m(x0), y0).backward()
+        opt.step()
     v0 = next(b.parameters())._version
     for i in range(4):
         x = torch.randn((2, 1, 64, 64, 16), generator=g).to(_dev())
@@ -399,7 +406,7 @@ def test_graphed_train_step_matches_eager_steps():
         oa.step()
         lb = graphed(x, y)
         assert abs(la.item() - lb.item()) < 1e-4 * max(1.0, abs(la.item())), (i, la.item(), lb.item())
-    assert oa.param_groups[0]["step"] == ob.param_groups[0]["step"] == 4
+    assert oa.param_groups[0]["step"] == ob.param_groups[0]["step"] == 5
     assert next(b.parameters())._version > v0
     # Adam normalises the update to ~lr per step whatever the gradient's size, so an element whose gradient is at the
     # rounding level of the atomics may move differently: compare the bulk tightly and bound the stragglers by the
@@ -408,7 +415,7 @@ def test_graphed_train_step_matches_eager_steps():
     assert (d > 1e-4).float().mean().item() < 0.01, (d > 1e-4).float().mean().item()
     assert d.max().item() < 8e-3, d.max().item()
     for (n1, b1), (_, b2) in zip(a.named_buffers(), b.named_buffers()):
-        assert (b1.float() - b2.float()).abs().max().item() < 1e-4 * max(1.0, b1.float().abs().max().item()), n1
+        assert (b1.float() - b2.float()).abs().max().item() < 1e-3 * max(1.0, b1.float().abs().max().item()), n1
 
 
 # ---- two ranks over NCCL ----------------------------------------------------------------------------------------

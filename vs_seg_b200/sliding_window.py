@@ -157,11 +157,11 @@ class _Program:
         self.imap = imap
         cell = self.cell.data_ptr()
         groups = [jobs[g0:g0 + group] for g0 in range(0, len(jobs), group)]
-        # VSSEG_SW_STREAMS=2: two window groups whose destination regions are disjoint run concurrently on two streams
+        # Two window groups whose destination regions are disjoint run concurrently on two streams (VSSEG_SW_STREAMS=1: off)
         # (two plans with their own activation buffers; the latency-bound coarse levels of one group overlap the
         # bandwidth-bound fine levels of the other).  Phases are joined before the next pair starts, so overlapping
         # windows are still blended in a fixed order (no atomics needed).
-        self.streams = 2 if (os.environ.get("VSSEG_SW_STREAMS", "1") == "2" and not self.peer and len(groups) >= 2) else 1
+        self.streams = 2 if (os.environ.get("VSSEG_SW_STREAMS", "2") == "2" and not self.peer and len(groups) >= 2) else 1
         self.side = torch.cuda.Stream(dev) if self.streams == 2 else None
         phases = self._pair_groups(groups, roi_size) if self.streams == 2 else [[i] for i in range(len(groups))]
         self.calls = []   # (plan, srcs, dsts)
@@ -284,7 +284,7 @@ def _program(model, inputs, roi_size, jobs, imap, image_size, extra, peer=False)
     """Cached _Program for (model weights, volume layout, geometry, shard)."""
     key = (id(model), model._weights_version(), tuple(inputs.shape), tuple(inputs.stride()), str(inputs.device),
            tuple(roi_size), extra, os.environ.get("VSSEG_SW_GROUP", "8"), os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"),
-           os.environ.get("VSSEG_SW_GRAPH", "1"), os.environ.get("VSSEG_SW_STREAMS", "1"), bool(peer))
+           os.environ.get("VSSEG_SW_GRAPH", "1"), os.environ.get("VSSEG_SW_STREAMS", "2"), bool(peer))
     prog = _PROGRAMS.get(key)
     if prog is None:
         if len(_PROGRAMS) >= 3:   # each program owns an accumulator volume and a captured graph

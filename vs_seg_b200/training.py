@@ -693,10 +693,17 @@ class GraphedTrainStep:
             g["step"] = st
 
     def _capture(self, inputs, labels):
+        import gc
         dev = inputs.device
         sx, sy = inputs.detach().clone(), labels.detach().clone()
-        # warm-up passes on a side stream (lazy initialisation, allocator pools, function attributes must not happen inside
-        # the capture); they are real steps on this batch, so the training state is put back afterwards
+        # autograd caches one AccumulateGrad node per parameter for as long as a graph that uses it is alive, and runs it
+        # on the stream it was created on: nodes left over from earlier eager steps (kept alive by model.att_maps or by a
+        # loss the caller still holds) would pull the legacy stream into the capture and invalidate it.  Drop our own
+        # reference, and run warm-up and capture on ONE side stream so the fresh nodes belong to the capture's stream.
+        self.model.att_maps = []
+        gc.collect()
+        # warm-up passes (lazy initialisation, allocator pools, function attributes must not happen inside the capture)
+        # are real steps on this batch, so the training state is put back afterwards
         snap = self._snapshot()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -706,9 +713,12 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._restore(snap)
+        self.model.att_maps = []
+        torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
             loss = self._eager(sx, sy)
+        self.model.att_maps = []   # the captured forward's maps are graph-private memory: do not hand them out
         return {"graph": graph, "x": sx, "y": sy, "loss": loss}
 
     def __call__(self, inputs, labels):
