@@ -419,6 +419,39 @@ def test_graphed_train_step_matches_eager_steps():
         assert (b1.float() - b2.float()).abs().max().item() < 5e-3 * max(1.0, b1.float().abs().max().item()), n1
 
 
+def test_train_mode_dropout_mask_statistics_and_backward_consistency():
+    """Dropout inside the native train-mode block (reference convolutions.py:148-156: Conv -> BN -> Dropout -> PReLU):
+    the keep fraction is 1 - p, kept values are scaled by 1/(1-p), and the backward pass regenerates exactly the mask of
+    the forward pass - checked by replaying the block in torch with the mask read off the native output."""
+    import copy
+    from params.networks.blocks.convolutions import Convolution
+    p_drop = 0.25
+    torch.manual_seed(7)
+    blk = Convolution(3, 16, 32, strides=1, kernel_size=(3, 3, 3), act="PRELU", norm="BATCH", dropout=p_drop)
+    ref = copy.deepcopy(blk).train()
+    nat = blk.to(_dev()).train()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((2, 16, 8, 8, 128), generator=g)
+    gy = torch.randn((2, 32, 8, 8, 128), generator=g)
+    xn = x.to(_dev()).requires_grad_(True)
+    yn = nat(xn)
+    yn.backward(gy.to(_dev()))
+    y = yn.detach().cpu()
+    keep = (y != 0)
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p_drop)) < 5e-3, frac
+    # torch replay with the same mask
+    xr = x.clone().requires_grad_(True)
+    u = ref.norm(ref.conv(xr))
+    yr = torch.nn.functional.prelu(u * keep.float() / (1 - p_drop), ref.act.weight)
+    yr.backward(gy)
+    assert (y - yr.detach()).abs().max().item() < 2e-3 * max(1.0, yr.abs().max().item())
+    assert (xn.grad.cpu() - xr.grad).abs().max().item() < 3e-2 * xr.grad.abs().max().item()
+    for (n1, p1), (_, p2) in zip(ref.named_parameters(), nat.named_parameters()):
+        err = (p2.grad.cpu() - p1.grad).abs().max().item()
+        assert err < (6e-2 if p1.numel() == 1 else 3e-2) * p1.grad.abs().max().item() + 1e-6, (n1, err)
+
+
 # ---- two ranks over NCCL ----------------------------------------------------------------------------------------
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
 def test_two_rank_nccl_sharded_inference_equals_one_gpu(tmp_path):

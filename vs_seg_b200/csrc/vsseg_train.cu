@@ -28,6 +28,28 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 // dropout keep-mask: a counter-based hash of (seed, logical NCDHW element index); the same function is
 // evaluated in forward and backward, so no mask is stored
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// the 8 keep-scales of one (batch, channel group, voxel) triple from TWO 64-bit hashes (16 bits per element: p is honoured
+// to 2^-16); one hash per element made the BatchNorm/activation kernels ALU-bound (31-36 % of the DRAM peak under ncu)
+__device__ __forceinline__ void keep_scale8(uint64_t seed, uint64_t group, float p, float (&ks)[8]) {
+    if (p <= 0.f) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ks[k] = 1.f;
+        return;
+    }
+    const uint64_t h0 = mix64(seed + (2 * group) * 0x9E3779B97F4A7C15ull), h1 = mix64(seed + (2 * group + 1) * 0x9E3779B97F4A7C15ull);
+    const uint32_t thr = (uint32_t)(p * 65536.0f);
+    const float inv = 1.0f / (1.0f - p);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t u = (uint32_t)(((k < 4 ? h0 : h1) >> (16 * (k & 3))) & 0xFFFFu);
+        ks[k] = u >= thr ? inv : 0.f;
+    }
+}
 __device__ __forceinline__ float keep_scale(uint64_t seed, uint64_t elem, float p) {
     if (p <= 0.f) return 1.f;
     uint64_t z = seed + elem * 0x9E3779B97F4A7C15ull;
@@ -66,8 +88,8 @@ __device__ __forceinline__ void g8_store(const vsseg_act8& t, int b, int cg, int
 // ---- batch statistics ----------------------------------------------------------------------------------
 // grid.y = channel group; every block reduces a slice of (b, voxel) and adds 8 sums + 8 sums of squares
 __global__ void __launch_bounds__(256) bn_stats_kernel(vsseg_act8 x, double* __restrict__ sums) {
-    const int cg = blockIdx.y;
-    const int64_t nvox = (int64_t)x.X * x.Y * x.Z, total = nvox * x.B;
+    const int cg = blockIdx.y, b = blockIdx.z;
+    const int64_t nvox = (int64_t)x.X * x.Y * x.Z;
     float s[8], q[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) s[c] = q[c] = 0.f;
@@ -75,9 +97,9 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(vsseg_act8 x, double* __r
 #pragma unroll
     for (int c = 0; c < 8; ++c) ds[c] = dq[c] = 0.0;
     int n = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvox; i += (int64_t)gridDim.x * blockDim.x) {
         float f[8];
-        g8_load(x, (int)(i / nvox), cg, i % nvox, nvox, f);
+        g8_load(x, b, cg, i, nvox, f);
 #pragma unroll
         for (int c = 0; c < 8; ++c) { s[c] += f[c]; q[c] += f[c] * f[c]; }
         if (++n == 64) {  // bounded fp32 partials, merged in fp64
@@ -130,23 +152,25 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(vsseg_act8 c, vsseg_act
                                                          int has_res) {
     const float slope = __ldg(slope_p);   // the PReLU parameter is read on the device: no host copy, graph-capturable
     if (seed_base) seed += __ldg(reinterpret_cast<const unsigned long long*>(seed_base));
-    const G8 it(c);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < it.total; i += (int64_t)gridDim.x * blockDim.x) {
-        int b, cg;
-        int64_t v;
-        it.split(i, b, cg, v);
-        float f[8], r[8];
-        g8_load(c, b, cg, v, it.nvox, f);
-        if (has_res) g8_load(res, b, cg, v, it.nvox, r);
+    // grid.y = (batch, channel group): no index arithmetic per element, the 16 per-channel constants live in registers
+    const int CG = c.C / 8, b = blockIdx.y / CG, cg = blockIdx.y % CG;
+    const int64_t nvox = (int64_t)c.X * c.Y * c.Z;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = __ldg(stats + cg * 8 + k); sh[k] = __ldg(stats + c.C + cg * 8 + k); }
+    const uint64_t gbase = (uint64_t)blockIdx.y * (uint64_t)nvox;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+        float f[8], r[8], ks[8];
+        g8_load(c, b, cg, v, nvox, f);
+        if (has_res) g8_load(res, b, cg, v, nvox, r);
+        keep_scale8(seed, gbase + (uint64_t)v, drop_p, ks);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int ch = cg * 8 + k;
-            float u = f[k] * __ldg(stats + ch) + __ldg(stats + c.C + ch);
-            u *= keep_scale(seed, ((uint64_t)b * c.C + ch) * (uint64_t)it.nvox + (uint64_t)v, drop_p);
+            float u = fmaf(f[k], sc[k], sh[k]) * ks[k];
             u = u >= 0.f ? u : u * slope;
             f[k] = has_res ? u + r[k] : u;
         }
-        g8_store(y, b, cg, v, it.nvox, f);
+        g8_store(y, b, cg, v, nvox, f);
     }
 }
 
@@ -156,31 +180,34 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(vsseg_act8 c, vs
                                                                 const uint64_t* __restrict__ seed_base, double* __restrict__ sums) {
     const float slope = __ldg(slope_p);
     if (seed_base) seed += __ldg(reinterpret_cast<const unsigned long long*>(seed_base));
-    const int cg = blockIdx.y;
-    const int64_t nvox = (int64_t)c.X * c.Y * c.Z, total = nvox * c.B;
+    const int cg = blockIdx.y, b = blockIdx.z, CG = c.C / 8;
+    const int64_t nvox = (int64_t)c.X * c.Y * c.Z;
     float s[8], q[8], da = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
     double ds[8], dq[8], dda = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) ds[k] = dq[k] = 0.0;
+    float sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ch = cg * 8 + k;
+        sc[k] = __ldg(stats + ch); sh[k] = __ldg(stats + c.C + ch); mu[k] = __ldg(stats + 2 * c.C + ch); rs[k] = __ldg(stats + 3 * c.C + ch);
+    }
+    const uint64_t gbase = ((uint64_t)b * CG + cg) * (uint64_t)nvox;
     int n = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int b = (int)(i / nvox);
-        const int64_t v = i % nvox;
-        float f[8], g[8];
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+        float f[8], g[8], ks[8];
         g8_load(c, b, cg, v, nvox, f);
         g8_load(dy, b, cg, v, nvox, g);
+        keep_scale8(seed, gbase + (uint64_t)v, drop_p, ks);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int ch = cg * 8 + k;
-            const float u = f[k] * __ldg(stats + ch) + __ldg(stats + c.C + ch);
-            const float ks = keep_scale(seed, ((uint64_t)b * c.C + ch) * (uint64_t)nvox + (uint64_t)v, drop_p);
-            const float w = u * ks;                       // PReLU input
+            const float w = fmaf(f[k], sc[k], sh[k]) * ks[k];   // PReLU input
             const float dv = w >= 0.f ? g[k] : g[k] * slope;
             if (w < 0.f) da += g[k] * w;
-            const float du = dv * ks;
-            const float xhat = (f[k] - __ldg(stats + 2 * c.C + ch)) * __ldg(stats + 3 * c.C + ch);
+            const float du = dv * ks[k];
+            const float xhat = (f[k] - mu[k]) * rs[k];
             s[k] += du;
             q[k] += du * xhat;
         }
@@ -218,27 +245,29 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(vsseg_act8 c, vss
                                                                const uint64_t* __restrict__ seed_base, vsseg_act8 dc) {
     const float slope = __ldg(slope_p);
     if (seed_base) seed += __ldg(reinterpret_cast<const unsigned long long*>(seed_base));
-    const G8 it(c);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < it.total; i += (int64_t)gridDim.x * blockDim.x) {
-        int b, cg;
-        int64_t v;
-        it.split(i, b, cg, v);
-        float f[8], g[8];
-        g8_load(c, b, cg, v, it.nvox, f);
-        g8_load(dy, b, cg, v, it.nvox, g);
+    const int CG = c.C / 8, b = blockIdx.y / CG, cg = blockIdx.y % CG;
+    const int64_t nvox = (int64_t)c.X * c.Y * c.Z;
+    float sc[8], sh[8], mu[8], rs[8], mb[8], mg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ch = cg * 8 + k;
+        sc[k] = __ldg(stats + ch); sh[k] = __ldg(stats + c.C + ch); mu[k] = __ldg(stats + 2 * c.C + ch); rs[k] = __ldg(stats + 3 * c.C + ch);
+        mb[k] = (float)(sums[ch] * inv_count); mg[k] = (float)(sums[c.C + ch] * inv_count);
+    }
+    const uint64_t gbase = (uint64_t)blockIdx.y * (uint64_t)nvox;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+        float f[8], g[8], ks[8];
+        g8_load(c, b, cg, v, nvox, f);
+        g8_load(dy, b, cg, v, nvox, g);
+        keep_scale8(seed, gbase + (uint64_t)v, drop_p, ks);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int ch = cg * 8 + k;
-            const float sc = __ldg(stats + ch);
-            const float u = f[k] * sc + __ldg(stats + c.C + ch);
-            const float ks = keep_scale(seed, ((uint64_t)b * c.C + ch) * (uint64_t)it.nvox + (uint64_t)v, drop_p);
-            const float w = u * ks;
-            const float du = (w >= 0.f ? g[k] : g[k] * slope) * ks;
-            const float xhat = (f[k] - __ldg(stats + 2 * c.C + ch)) * __ldg(stats + 3 * c.C + ch);
-            const float mb = (float)(sums[ch] * inv_count), mg = (float)(sums[c.C + ch] * inv_count);
-            f[k] = sc * (du - mb - xhat * mg);
+            const float w = fmaf(f[k], sc[k], sh[k]) * ks[k];
+            const float du = (w >= 0.f ? g[k] : g[k] * slope) * ks[k];
+            const float xhat = (f[k] - mu[k]) * rs[k];
+            f[k] = sc[k] * (du - mb[k] - xhat * mg[k]);
         }
-        g8_store(dc, b, cg, v, it.nvox, f);
+        g8_store(dc, b, cg, v, nvox, f);
     }
 }
 
@@ -669,6 +698,15 @@ static unsigned ew_grid(int64_t total, int block) {
     int64_t need = (total + block - 1) / block, cap = (int64_t)sms * 16;
     return (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
 }
+// x extent of a (x, rows) grid of 256-thread blocks: about 16 blocks per SM in total, at least one block per row
+static unsigned ew_grid_2d(int64_t nvox, int rows) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t need = (nvox + 255) / 256, cap = ((int64_t)sms * 16 + rows - 1) / rows;
+    if (cap < 1) cap = 1;
+    return (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
+}
 static bool a8ok(const vsseg_act8* t) {
     return t && t->hi && t->C > 0 && t->C % 8 == 0 && t->B > 0 && t->X > 0 && t->Y > 0 && t->Z > 0;
 }
@@ -684,8 +722,8 @@ extern "C" {
 
 int vsseg_bn_stats(const vsseg_act8* x, double* sums, void* stream) {
     VSSEG_REQUIRE(a8ok(x) && sums, "bn_stats: bad arguments");
-    const int64_t total = (int64_t)x->B * x->X * x->Y * x->Z;
-    dim3 grid(ew_grid(total, 256 * 8), (unsigned)(x->C / 8));
+    const int64_t nvox = (int64_t)x->X * x->Y * x->Z;
+    dim3 grid(ew_grid(nvox, 256 * 8), (unsigned)(x->C / 8), (unsigned)x->B);
     bn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*x, sums);
     return check_launch("bn_stats");
 }
@@ -704,8 +742,12 @@ int vsseg_bn_act_fwd(const vsseg_act8* c, const vsseg_act8* y, const float* stat
     VSSEG_REQUIRE(a8ok(c) && a8ok(y) && same_shape(c, y) && stats && slope, "bn_act_fwd: bad arguments");
     VSSEG_REQUIRE(!residual || (a8ok(residual) && same_shape(residual, c)), "bn_act_fwd: residual shape mismatch");
     VSSEG_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "bn_act_fwd: dropout probability must be in [0,1)");
-    const int64_t total = (int64_t)c->B * (c->C / 8) * c->X * c->Y * c->Z;
-    bn_act_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(*c, *y, stats, slope, drop_p, seed, seed_base,
+    // grid.y = (batch, channel group); x covers the voxels with a few per thread so every SM holds several blocks
+    const int64_t nvox = (int64_t)c->X * c->Y * c->Z;
+    const int rows = c->B * (c->C / 8);
+    VSSEG_REQUIRE(rows <= 65535, "bn_act_fwd: batch x channel groups exceeds the grid limit");
+    dim3 grid(ew_grid_2d(nvox, rows), (unsigned)rows);
+    bn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*c, *y, stats, slope, drop_p, seed, seed_base,
                                                                             residual ? *residual : *c, residual ? 1 : 0);
     return check_launch("bn_act_fwd");
 }
@@ -713,8 +755,8 @@ int vsseg_bn_act_fwd(const vsseg_act8* c, const vsseg_act8* y, const float* stat
 int vsseg_bn_act_bwd_reduce(const vsseg_act8* c, const vsseg_act8* dy, const float* stats, const float* slope, float drop_p,
                             uint64_t seed, const uint64_t* seed_base, double* sums, void* stream) {
     VSSEG_REQUIRE(a8ok(c) && a8ok(dy) && same_shape(c, dy) && stats && sums && slope, "bn_act_bwd_reduce: bad arguments");
-    const int64_t total = (int64_t)c->B * c->X * c->Y * c->Z;
-    dim3 grid(ew_grid(total, 256 * 8), (unsigned)(c->C / 8));
+    const int64_t nvox = (int64_t)c->X * c->Y * c->Z;
+    dim3 grid(ew_grid(nvox, 256 * 8), (unsigned)(c->C / 8), (unsigned)c->B);
     bn_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*c, *dy, stats, slope, drop_p, seed, seed_base, sums);
     return check_launch("bn_act_bwd_reduce");
 }
@@ -725,7 +767,11 @@ int vsseg_bn_act_bwd_apply(const vsseg_act8* c, const vsseg_act8* dy, const floa
     VSSEG_REQUIRE(a8ok(c) && a8ok(dy) && a8ok(dc) && same_shape(c, dy) && same_shape(c, dc) && stats && sums && slope,
                   "bn_act_bwd_apply: bad arguments");
     const int64_t count = (int64_t)c->B * c->X * c->Y * c->Z;
-    bn_act_bwd_apply_kernel<<<ew_grid(count * (c->C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+    const int64_t nvox = (int64_t)c->X * c->Y * c->Z;
+    const int rows = c->B * (c->C / 8);
+    VSSEG_REQUIRE(rows <= 65535, "bn_act_bwd_apply: batch x channel groups exceeds the grid limit");
+    dim3 grid(ew_grid_2d(nvox, rows), (unsigned)rows);
+    bn_act_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         *c, *dy, stats, sums, 1.0 / (double)count, slope, drop_p, seed, seed_base, *dc);
     return check_launch("bn_act_bwd_apply");
 }
