@@ -382,7 +382,7 @@ def test_graphed_train_step_matches_eager_steps():
                       kernel_sizes=unet_oracle.KERNEL_SIZES, sample_kernel_sizes=unet_oracle.SAMPLE_KERNEL_SIZES,
                       num_res_units=2, norm="BATCH", dropout=0.0).to(_dev()).train()
     b = copy.deepcopy(a)
-    oa, ob = FusedAdam(a.parameters(), lr=1e-3, weight_decay=1e-7), FusedAdam(b.parameters(), lr=1e-3, weight_decay=1e-7)
+    oa, ob = FusedAdam(a.parameters(), lr=1e-4, weight_decay=1e-7), FusedAdam(b.parameters(), lr=1e-4, weight_decay=1e-7)
     crit = Dice_spvPA(to_onehot_y=True, softmax=True)
     graphed = GraphedTrainStep(b, crit, ob)
     g = torch.Generator().manual_seed(9)
@@ -399,7 +399,7 @@ def test_graphed_train_step_matches_eager_steps():
         y = (torch.rand((2, 1, 64, 64, 16), generator=g) > 0.7).float().to(_dev())
         if i == 2:
             for opt in (oa, ob):
-                opt.param_groups[0]["lr"] = 2.5e-4
+                opt.param_groups[0]["lr"] = 2.5e-5
         oa.zero_grad()
         la = crit(a(x), y)
         la.backward()
@@ -412,9 +412,9 @@ def test_graphed_train_step_matches_eager_steps():
     # rounding level of the atomics may move differently: compare the bulk tightly and bound the stragglers by the
     # total step length (4 steps x lr)
     d = torch.cat([(p1 - p2).detach().abs().reshape(-1) for p1, p2 in zip(a.parameters(), b.parameters())])
-    assert (d > 1e-4).float().mean().item() < 0.01, (d > 1e-4).float().mean().item()
-    assert d.max().item() < 8e-3, d.max().item()
-    # the running statistics of the deep levels see the accumulated parameter differences above (measured 1.2e-3)
+    assert (d > 1e-5).float().mean().item() < 0.01, (d > 1e-5).float().mean().item()
+    assert d.max().item() < 8e-4, d.max().item()
+    # the running statistics of the deep levels see the accumulated parameter differences above
     for (n1, b1), (_, b2) in zip(a.named_buffers(), b.named_buffers()):
         assert (b1.float() - b2.float()).abs().max().item() < 5e-3 * max(1.0, b1.float().abs().max().item()), n1
 
@@ -447,9 +447,11 @@ def test_train_mode_dropout_mask_statistics_and_backward_consistency():
     yr.backward(gy)
     assert (y - yr.detach()).abs().max().item() < 2e-3 * max(1.0, yr.abs().max().item())
     assert (xn.grad.cpu() - xr.grad).abs().max().item() < 3e-2 * xr.grad.abs().max().item()
+    gmax_all = max(p1.grad.abs().max().item() for p1 in ref.parameters())
     for (n1, p1), (_, p2) in zip(ref.named_parameters(), nat.named_parameters()):
         err = (p2.grad.cpu() - p1.grad).abs().max().item()
-        assert err < (6e-2 if p1.numel() == 1 else 3e-2) * p1.grad.abs().max().item() + 1e-6, (n1, err)
+        # (the conv bias cancels in train-mode BatchNorm: its gradient is rounding noise on both sides)
+        assert err < (6e-2 if p1.numel() == 1 else 3e-2) * p1.grad.abs().max().item() + 1e-4 * gmax_all, (n1, err)
 
 
 # ---- two ranks over NCCL ----------------------------------------------------------------------------------------
