@@ -97,12 +97,29 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(vsseg_act8 x, double* __r
 #pragma unroll
     for (int c = 0; c < 8; ++c) ds[c] = dq[c] = 0.0;
     int n = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvox; i += (int64_t)gridDim.x * blockDim.x) {
-        float f[8];
-        g8_load(x, b, cg, i, nvox, f);
+    // four independent 32-byte groups in flight per thread (one load pair per iteration left the reduction at a third
+    // of the DRAM peak under ncu)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvox; i += 4 * stride) {
+        uint4 h[4], l[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { s[c] += f[c]; q[c] += f[c] * f[c]; }
-        if (++n == 64) {  // bounded fp32 partials, merged in fp64
+        for (int u = 0; u < 4; ++u) {
+            const int64_t v = i + u * stride;
+            if (v < nvox) {
+                const __nv_bfloat16* p = g8_ptr(x, b, cg, v, nvox);
+                h[u] = ldg128(p);
+                l[u] = ldg128(p + x.lo_offset);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i + u * stride >= nvox) break;
+            float f[8];
+            unpack8(h[u], l[u], f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { s[c] += f[c]; q[c] += f[c] * f[c]; }
+        }
+        if (++n == 16) {  // bounded fp32 partials (64 values), merged in fp64
 #pragma unroll
             for (int c = 0; c < 8; ++c) { ds[c] += s[c]; dq[c] += q[c]; s[c] = q[c] = 0.f; }
             n = 0;
@@ -196,22 +213,39 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(vsseg_act8 c, vs
     }
     const uint64_t gbase = ((uint64_t)b * CG + cg) * (uint64_t)nvox;
     int n = 0;
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
-        float f[8], g[8], ks[8];
-        g8_load(c, b, cg, v, nvox, f);
-        g8_load(dy, b, cg, v, nvox, g);
-        keep_scale8(seed, gbase + (uint64_t)v, drop_p, ks);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v0 < nvox; v0 += 2 * stride) {
+        uint4 ch[2], cl[2], dh[2], dl[2];   // two independent groups (8 x 16 B) in flight per thread
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float w = fmaf(f[k], sc[k], sh[k]) * ks[k];   // PReLU input
-            const float dv = w >= 0.f ? g[k] : g[k] * slope;
-            if (w < 0.f) da += g[k] * w;
-            const float du = dv * ks[k];
-            const float xhat = (f[k] - mu[k]) * rs[k];
-            s[k] += du;
-            q[k] += du * xhat;
+        for (int u = 0; u < 2; ++u) {
+            const int64_t v = v0 + u * stride;
+            if (v < nvox) {
+                const __nv_bfloat16* pc = g8_ptr(c, b, cg, v, nvox);
+                const __nv_bfloat16* pd = g8_ptr(dy, b, cg, v, nvox);
+                ch[u] = ldg128(pc); cl[u] = ldg128(pc + c.lo_offset);
+                dh[u] = ldg128(pd); dl[u] = ldg128(pd + dy.lo_offset);
+            }
         }
-        if (++n == 64) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t v = v0 + u * stride;
+            if (v >= nvox) break;
+            float f[8], g[8], ks[8];
+            unpack8(ch[u], cl[u], f);
+            unpack8(dh[u], dl[u], g);
+            keep_scale8(seed, gbase + (uint64_t)v, drop_p, ks);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float w = fmaf(f[k], sc[k], sh[k]) * ks[k];   // PReLU input
+                const float dv = w >= 0.f ? g[k] : g[k] * slope;
+                if (w < 0.f) da += g[k] * w;
+                const float du = dv * ks[k];
+                const float xhat = (f[k] - mu[k]) * rs[k];
+                s[k] += du;
+                q[k] += du * xhat;
+            }
+        }
+        if (++n == 32) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) { ds[k] += s[k]; dq[k] += q[k]; s[k] = q[k] = 0.f; }
             dda += da; da = 0.f;
