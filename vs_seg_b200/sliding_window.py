@@ -161,9 +161,14 @@ class _Program:
         # (two plans with their own activation buffers; the latency-bound coarse levels of one group overlap the
         # bandwidth-bound fine levels of the other).  Phases are joined before the next pair starts, so overlapping
         # windows are still blended in a fixed order (no atomics needed).
-        self.streams = 2 if (os.environ.get("VSSEG_SW_STREAMS", "2") == "2" and not self.peer and len(groups) >= 2) else 1
+        self.streams = 2 if (os.environ.get("VSSEG_SW_STREAMS", "2") == "2" and len(groups) >= 2) else 1
         self.side = torch.cuda.Stream(dev) if self.streams == 2 else None
-        phases = self._pair_groups(groups, roi_size) if self.streams == 2 else [[i] for i in range(len(groups))]
+        if self.streams == 1:
+            phases = [[i] for i in range(len(groups))]
+        elif self.peer:   # atomic blend: any two groups may run concurrently
+            phases = [list(range(i, min(i + 2, len(groups)))) for i in range(0, len(groups), 2)]
+        else:
+            phases = self._pair_groups(groups, roi_size)
         self.calls = []   # (plan, srcs, dsts)
         self.phases = []  # lists of 1 or 2 indices into self.calls
         for ph in phases:
