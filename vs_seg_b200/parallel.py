@@ -23,6 +23,7 @@ from . import sliding_window as sw
 
 
 _PEER: dict = {}
+_PEER_DISABLED = False   # set (on every rank together) when CUDA IPC turned out to be unavailable
 
 
 def _peer_accumulator(shape, device, group, dst):
@@ -39,7 +40,7 @@ def _peer_accumulator(shape, device, group, dst):
 
 
 def _use_peer(inputs, predictor):
-    return (os.environ.get("VSSEG_SW_PEER", "1") != "0" and inputs.is_cuda and inputs.dim() == 5
+    return (not _PEER_DISABLED and os.environ.get("VSSEG_SW_PEER", "1") != "0" and inputs.is_cuda and inputs.dim() == 5
             and sw._native_model(predictor) is not None and dist.get_backend() == "nccl")
 
 
@@ -62,17 +63,22 @@ def sharded_sliding_window_inference(inputs, roi_size, sw_batch_size, predictor,
                                                            padding_mode, cval, sw_batch_size)
         return sw.finalize(acc, cnt, lows, img, label=label, return_mask=return_mask)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    pa = None
     if _use_peer(inputs, predictor):
-        box = {}
-
-        def peer_acc(shape):
-            box["acc"] = _peer_accumulator(shape, inputs.device, group, dst)
-            return box["acc"].begin()
-
+        global _PEER_DISABLED
+        from .peer import PeerUnavailable
+        model = sw._native_model(predictor)
+        nd = inputs.dim() - 2
+        roi = (roi_size,) * nd if isinstance(roi_size, int) else tuple(roi_size)
+        padded = tuple(max(int(i), int(r) if r and r > 0 else int(i)) for i, r in zip(inputs.shape[2:], roi))
+        try:   # collective: every rank maps the destination's buffers, or every rank falls back to the reduce path
+            pa = _peer_accumulator((inputs.shape[0], model.out_channels) + padded, inputs.device, group, dst)
+        except PeerUnavailable:
+            _PEER_DISABLED = True
+    if pa is not None:
         _, cnt, lows, img = sw.sliding_window_accumulate(inputs, roi_size, predictor, overlap, mode, sigma_scale,
                                                          padding_mode, cval, sw_batch_size, window_shard=(rank, world),
-                                                         peer_acc=peer_acc)
-        pa = box["acc"]
+                                                         peer_acc=lambda shape: pa.begin())
         pa.arrive()
         res = None
         if rank == dst:

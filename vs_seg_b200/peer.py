@@ -41,6 +41,10 @@ def _alias(ptr, shape, dtype, device):
     return torch.as_tensor(_DevMem(ptr, shape, typestr), device=device)
 
 
+class PeerUnavailable(RuntimeError):
+    """CUDA IPC mapping of the destination's accumulator failed on some rank (every rank raises together)."""
+
+
 class PeerAccumulator:
     def __init__(self, shape, device, group=None, dst=0):
         self.lib = _lib.load()
@@ -53,25 +57,38 @@ class PeerAccumulator:
         nflags = 2 * self.world + 2
         sizes = [nbytes, nbytes, 8 * max(nflags, 16)]
         self._owned, self._opened = [], []
-        handles = None
+        handles, ok = None, True
         if self.rank == dst:
             handles = []
-            for sz in sizes:
-                p, h = C.c_void_p(), C.create_string_buffer(64)
-                _lib.check(self.lib.vsseg_peer_alloc(sz, C.byref(p), h), "peer_alloc")
-                self._owned.append(p.value)
-                handles.append(h.raw)
+            try:
+                for sz in sizes:
+                    p, h = C.c_void_p(), C.create_string_buffer(64)
+                    _lib.check(self.lib.vsseg_peer_alloc(sz, C.byref(p), h), "peer_alloc")
+                    self._owned.append(p.value)
+                    handles.append(h.raw)
+            except _lib.NativeLibraryError:
+                handles, ok = None, False
         box = [handles]
         dist.broadcast_object_list(box, src=dst, group=group)
-        if self.rank == dst:
-            ptrs = list(self._owned)
-        else:
+        ptrs = list(self._owned)
+        if box[0] is None:
+            ok = False
+        elif self.rank != dst:
             ptrs = []
-            for h in box[0]:
-                p = C.c_void_p()
-                _lib.check(self.lib.vsseg_peer_open(C.create_string_buffer(h, 64), C.byref(p)), "peer_open")
-                self._opened.append(p.value)
-                ptrs.append(p.value)
+            try:
+                for h in box[0]:
+                    p = C.c_void_p()
+                    _lib.check(self.lib.vsseg_peer_open(C.create_string_buffer(h, 64), C.byref(p)), "peer_open")
+                    self._opened.append(p.value)
+                    ptrs.append(p.value)
+            except _lib.NativeLibraryError:
+                ok = False
+        # every rank must agree: one failed mapping sends all of them to the reduce path
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise PeerUnavailable("CUDA IPC mapping of the peer accumulator is not available on this node")
         self.acc_ptr = ptrs[:2]
         self.flags_ptr = ptrs[2]
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
