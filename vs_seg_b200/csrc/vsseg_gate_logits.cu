@@ -21,7 +21,14 @@
 namespace vsseg {
 
 constexpr int GL_TZ = 8;
-constexpr int GL_MAXL = 66;
+#ifndef VSSEG_GL_MAXL
+#define VSSEG_GL_MAXL 66
+#endif
+#ifndef VSSEG_GL_CTAS
+#define VSSEG_GL_CTAS 2
+#endif
+constexpr int GL_MAXL = VSSEG_GL_MAXL;   // y lines per CTA (incl. the two halo lines of an interior tile)
+constexpr int GL_CTAS = VSSEG_GL_CTAS;   // CTAs per SM the register budget is cut for
 constexpr int GL_MAXW = 16;
 constexpr int GL_CIN = 32;
 
@@ -38,7 +45,7 @@ struct GateLogitsArgs {
 };
 
 template <int COUT>
-__global__ void __launch_bounds__(GL_MAXL* GL_TZ, 2) gate_logits_kernel(const __grid_constant__ GateLogitsArgs a) {
+__global__ void __launch_bounds__(GL_MAXL* GL_TZ, GL_CTAS) gate_logits_kernel(const __grid_constant__ GateLogitsArgs a) {
     extern __shared__ float ex[];   // [2 buffers][ty = 0 | 2][tx][COUT][threads]
     constexpr int NCG = GL_CIN / 8;
     const int nthr = blockDim.x, tid = threadIdx.x;
@@ -194,7 +201,7 @@ extern "C" int vsseg_conv3d_gate_logits(const vsseg_act8* x, const vsseg_f32view
     a.sw_weight = sw_weight;
     a.atomic = atomic_blend ? 1 : 0;
     const int Y = x->Y, X = x->X;
-    a.ny = Y <= GL_MAXL ? 1 : (Y + 63) / 64;
+    a.ny = Y <= GL_MAXL ? 1 : (Y + GL_MAXL - 3) / (GL_MAXL - 2);
     a.TY = (Y + a.ny - 1) / a.ny;
     a.L = a.ny == 1 ? Y : a.TY + 2;
     a.nz = x->Z / GL_TZ;
@@ -204,7 +211,7 @@ extern "C" int vsseg_conv3d_gate_logits(const vsseg_act8* x, const vsseg_f32view
     // x segments: every segment re-projects one plane on either side, a CTA costs ~(XT + 2) planes; pick the
     // segmentation with the fewest plane-steps over the waves of 2 CTAs per SM
     static const int xt_env = getenv("VSSEG_GL_XT") ? atoi(getenv("VSSEG_GL_XT")) : 0;
-    const long base = (long)x->B * a.nz * a.ny, slots = 2L * sms;
+    const long base = (long)x->B * a.nz * a.ny, slots = (long)GL_CTAS * sms;
     long best_cost = -1;
     for (int nxs = 1; nxs <= (X + 3) / 4; ++nxs) {
         const int XT = (X + nxs - 1) / nxs;

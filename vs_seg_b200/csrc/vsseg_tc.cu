@@ -919,6 +919,7 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     static const double epi_unit = getenv("VSSEG_TC_EPI_UNIT") ? atof(getenv("VSSEG_TC_EPI_UNIT")) : 400.0;  // cycles per (accumulator, 16 columns) unit per warp
     int best_slots = 1;
     bool best_ts = false;
+    static const int nstage_max = getenv("VSSEG_TC_NSTAGE_MAX") ? atoi(getenv("VSSEG_TC_NSTAGE_MAX")) : 6;   // <= 8 (barrier arrays)
     // TS mode: stride-1 convs without z taps on 128-long z lines (box mode, every A view is one whole z line)
     // Measured (tools/ubench/mma_ts.cu, profiles/r02_*): a tcgen05.mma M=128 K=16 has an execution floor of ~45 cycles
     // for N <= 90 in BOTH modes (SS: max(45, 32 + N/4); TS: max(45, N/2)), so moving A to tensor memory only pays for
@@ -1010,7 +1011,7 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             const double cost = (double)((tiles + sms_ - 1) / sms_) * tile_cyc + 4000.0;
             if (cost < best_cost || (ts_env == 2 && ts && !best_ts)) {
                 best_cost = cost; best = YT; best_xt = XT; best_stage = stage; best_slots = slots;
-                best_nstage = nst > 6 ? 6 : nst;
+                best_nstage = nst > nstage_max ? nstage_max : nst;
                 best_ts = ts != 0;
             }
         }
