@@ -6,7 +6,10 @@ O=gpurun_out
 mkdir -p $O
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__issue_active.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,launch__grid_size,launch__block_size,launch__shared_mem_per_block_dynamic
 # 1. launch list of the bench command (per-launch times are cold-cache and serialised: compare SHARES, not absolutes)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${R}_launches_bench.csv \
+# (the timed region replays CUDA graphs: --graph-profiling node lists their kernel nodes one by one; the filter keeps the
+# repo's kernels and drops the torch element-wise kernels of the set-up)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node \
+    -k regex:'conv_tc|gate_logits|cin1|att_gate|sw_finalize|smallcout|conv_act8' -c 1600 --csv --log-file $O/${R}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > $O/${R}_bench_under_ncu.log 2>&1
 # 2. per-launch metrics of one window group (same plan as the timed region)
 export PROFILE_GROUP=8
