@@ -252,6 +252,14 @@ TC_CASES = [
     (1, 80, 96, (4, 4, 16), (3, 3, 3), (1, 1, 1), False),     # bottom level of a 128^3 patch: half-empty M tile
     (1, 80, 80, (8, 8, 32), (3, 3, 3), (2, 2, 2), False),     # downsample into the bottom level
     (1, 96, 80, (4, 4, 16), (3, 3, 3), (2, 2, 2), True),      # upsample out of the bottom level
+    # tiny z extents (shallow crops): LZ = 4, 2, 1 with 32..128 y lines per M tile, boxes at a padded 128-B stride
+    (4, 96, 80, (2, 2, 2), (3, 3, 3), (2, 2, 2), True),       # bottom upsample of a 64x64x16 window (smoke geometry)
+    (2, 80, 96, (3, 2, 2), (3, 3, 3), (1, 1, 1), False),      # LZ=2, z halo through per-dz boxes
+    (1, 64, 80, (6, 4, 4), (3, 3, 3), (2, 2, 2), False),      # downsample to Z=2
+    (1, 80, 96, (3, 2, 5), (3, 3, 3), (1, 1, 1), False),      # odd Z: LZ=1, one voxel per line
+    (1, 96, 80, (3, 2, 5), (3, 3, 3), (2, 2, 2), True),       # upsample from odd Z
+    (1, 80, 80, (6, 4, 10), (3, 3, 3), (2, 2, 2), False),     # downsample to odd Z
+    (1, 32, 48, (4, 4, 20), (3, 3, 1), (1, 1, 1), False),     # Z=20: LZ=4
 ]
 
 

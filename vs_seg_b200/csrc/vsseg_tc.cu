@@ -5,7 +5,8 @@
 // ResidualUnit shortcut fused as a second accumulator (convolutions.py:241-255).
 //
 // GEMM view.  An M tile is 128 positions of the "M grid" (the output grid of a conv, the INPUT grid
-// of a transposed conv): LY consecutive y lines x LZ consecutive z (LY*LZ = 128, LZ = min(Z,128)).
+// of a transposed conv): LY consecutive y lines x LZ consecutive z (LY*LZ = 128, LZ = the largest power of two <= 128
+// that divides Z).
 // N = a slice of Cout, K = Cin x taps walked as stages (16-channel chunk c, x tap j).  Operands
 // are the two bf16 planes of the act8 layout (value = hi + lo); every product is evaluated as
 // hi*hi + lo*hi + hi*lo ("bf16x3") into one fp32 TMEM accumulator, which keeps the network inside
@@ -956,9 +957,9 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             else if (strided) { nbox = KY * KZ; BY = YT * LY; BZ = LZ; }
             else { nbox = KZ; BY = YT * LY + 2 * hy; BZ = LZ; }
             if (!line && (BY * (strided ? g->sy : 1) > 256 || BZ * (strided ? g->sz : 1) > 256)) break;
-            const size_t box_bytes = (size_t)2 * BY * BZ * 16;
-            if (!line && nbox > 1 && box_bytes % 128) continue;   // every TMA box must land 128-byte aligned (tiny LZ)
-            const size_t a_plane = round_up((int)(nbox * box_bytes), 128);
+            // every TMA box must land 128-byte aligned: boxes of tiny-LZ tiles are spaced at a padded stride
+            const size_t box_bytes = (size_t)round_up(2 * BY * BZ * 16, 128);
+            const size_t a_plane = nbox * box_bytes;
             double mma_cyc = 0;
             {
                 TcGeom G{tr, strided, line, KY, KZ, LY, LZ, BZ, (int)g->sz, n_cta, sy_in, (uint32_t)box_bytes,
@@ -1023,21 +1024,22 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     else if (tr) { nbox = g->sz; BY = YT * LY + 1; BZ = LZ; }
     else if (strided) { nbox = KY * KZ; BY = YT * LY; BZ = LZ; }
     else { nbox = KZ; BY = YT * LY + 2 * hy; BZ = LZ; }
-    const uint32_t box_bytes = (uint32_t)(2 * BY * BZ * 16);
+    const uint32_t box_tx = (uint32_t)(2 * BY * BZ * 16);           // bytes one box moves
+    const uint32_t box_bytes = (uint32_t)round_up((int)box_tx, 128);   // distance between boxes of a stage
     a.out = *out;
     a.nchunk = in->C / 16;
     a.nj = tr ? 2 : KX;   // transposed: px=0 CTAs use j=0 only (see nj_eff below)
     a.nchunk2 = src2 ? src2->C / 16 : 0;
     a.nbox = nbox;
     a.nstage = best_nstage;
-    a.a_plane = (uint32_t)round_up((int)(nbox * box_bytes), 128);
+    a.a_plane = (uint32_t)(nbox * box_bytes);
     a.b_off = 2 * a.a_plane;
     a.b_bytes = b_bytes;
     a.b_plane = b_bytes / 2;
     a.b2_bytes = (uint32_t)(2 * n_cta * 32);
     a.b2_plane = a.b2_bytes / 2;
     a.stage_bytes = (uint32_t)best_stage;
-    a.box_tx = box_bytes;
+    a.box_tx = box_tx;
     a.lbo_a = (uint32_t)(BY * BZ * 16);
     a.lbo_b = (uint32_t)(KY * n_cta * 16);   // B region: [tz][khalf][ty'][n][8]
     a.lbo_b2 = (uint32_t)(n_cta * 16);
