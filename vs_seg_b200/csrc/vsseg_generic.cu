@@ -312,11 +312,11 @@ __global__ void __launch_bounds__(128) conv_cin1_k331_kernel(const Cin1Args a) {
     const int b = t / X;
     const int z = zt * 128 + threadIdx.x;
     if (z >= Z) return;
-    float acc[CIN1_YB][16];
+    float2 acc2[CIN1_YB][8];   // channel pairs: packed fp32 FMAs (fma.rn.f32x2), the kernel is instruction-bound
 #pragma unroll
     for (int v = 0; v < CIN1_YB; ++v)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[v][c] = 0.f;
+        for (int c = 0; c < 8; ++c) acc2[v][c] = make_float2(0.f, 0.f);
     const float* src = f32_base(a.in) + (int64_t)b * a.in.sb + (int64_t)z * a.in.sz;
 #pragma unroll
     for (int tx = 0; tx < 3; ++tx) {
@@ -335,11 +335,9 @@ __global__ void __launch_bounds__(128) conv_cin1_k331_kernel(const Cin1Args a) {
                 const float4 w = ws4[(tx * 3 + ty) * 4 + q];
 #pragma unroll
                 for (int v = 0; v < CIN1_YB; ++v) {
-                    const float s = sv[v + ty];
-                    acc[v][4 * q] = fmaf(s, w.x, acc[v][4 * q]);
-                    acc[v][4 * q + 1] = fmaf(s, w.y, acc[v][4 * q + 1]);
-                    acc[v][4 * q + 2] = fmaf(s, w.z, acc[v][4 * q + 2]);
-                    acc[v][4 * q + 3] = fmaf(s, w.w, acc[v][4 * q + 3]);
+                    const float2 s2 = make_float2(sv[v + ty], sv[v + ty]);
+                    acc2[v][2 * q] = __ffma2_rn(s2, make_float2(w.x, w.y), acc2[v][2 * q]);
+                    acc2[v][2 * q + 1] = __ffma2_rn(s2, make_float2(w.z, w.w), acc2[v][2 * q + 1]);
                 }
             }
     }
@@ -360,7 +358,8 @@ __global__ void __launch_bounds__(128) conv_cin1_k331_kernel(const Cin1Args a) {
             *reinterpret_cast<float4*>(sh + 4) = ep4[4 + g8 * 2 + 1];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float f = fmaf(acc[v][g8 * 8 + c], sc[c], sh[c]);
+                const float av = (c & 1) ? acc2[v][g8 * 4 + c / 2].y : acc2[v][g8 * 4 + c / 2].x;
+                const float f = fmaf(av, sc[c], sh[c]);
                 o[c] = fmaf(fminf(f, 0.f), sm1, f);   // PReLU / ReLU / identity
             }
             uint4 h, l;
