@@ -51,12 +51,19 @@ typedef struct {
  * (MONAI sliding_window_inference, reference call site VSparams.py:568-574) is re-targeted to another
  * volume by one 8-byte store.  Honoured by the forward kernels (vsseg_conv3d_cin1, vsseg_conv3d_tc*,
  * vsseg_conv3d_act8, vsseg_conv3d_smallcout, vsseg_conv3d_gate_logits, vsseg_att_gate); the layout
- * conversion and training entry points reject it. */
+ * conversion and training entry points reject it.
+ * `n_windows` > 1 makes the record the first of a WINDOW SET: n_windows contiguous vsseg_f32view records, each one
+ * window (B == 1) of the same volume (identical strides, extents and `indirect`), that together stand for a batch
+ * of n_windows items - batch item b is record b.  The windows of a sliding-window group (MONAI
+ * sliding_window_inference slices its windows out of one padded volume, call site VSparams.py:568-574) are read in
+ * place by ONE launch this way.  Honoured where stated (vsseg_conv3d_cin1 `in`, vsseg_conv3d_tc `res_src`);
+ * everything else requires n_windows <= 1. */
+#define VSSEG_MAX_WINDOWS 16
 typedef struct {
     float*  ptr;           /* element (b=0, c=0, x=0, y=0, z=0) of the region (byte offset if indirect) */
     int64_t sb, sc, sx, sy, sz;
     int32_t B, C, X, Y, Z;
-    int32_t reserved;      /* 0 */
+    int32_t n_windows;     /* 0 or 1: a plain view; n > 1: first record of a window set (see above) */
     const int64_t* indirect; /* NULL, or device cell holding the base address */
 } vsseg_f32view;
 
@@ -123,6 +130,7 @@ int vsseg_conv3d_act8(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
  *     (convolutions.py:241-255) accumulated in a second TMEM accumulator and added after the
  *     activation: out = act(BN(conv(in))) + shortcut_w * shortcut_src + shortcut_bias.
  *     shortcut_w: bf16 [n-slice][Csrc/16][plane][khalf][n_cta][8]; stride-1 convs only.
+ *   res_src may be a window set (vsseg_f32view.n_windows == out->B): batch item b adds the affine map of window b.
  */
 int vsseg_conv3d_tc_supported(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g,
                               int32_t n_split, const vsseg_act8* shortcut_src);
@@ -160,7 +168,8 @@ int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_con
                     void* stream);
 
 /* First encoder conv: 1-channel fp32 input (read in place from the volume) -> act8.
- * Replaces model.0.conv.unit0 (Conv3d(1,16,(3,3,1)) + BN + PReLU).  w: fp32 [taps][Cout]. */
+ * Replaces model.0.conv.unit0 (Conv3d(1,16,(3,3,1)) + BN + PReLU).  w: fp32 [taps][Cout].
+ * `in` may be a window set (vsseg_f32view.n_windows == out->B): every window of a sliding-window group in one launch. */
 int vsseg_conv3d_cin1(const vsseg_f32view* in, const vsseg_act8* out, const vsseg_conv_geom* g,
                       const float* w, const vsseg_epilogue* ep, void* stream);
 

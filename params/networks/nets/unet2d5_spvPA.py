@@ -136,12 +136,13 @@ class UNet2d5_spvPA(nn.Module):
         """The cached fused launch plan for eval-mode inference on [batch,1,*patch_size]
         (window_levels: see vs_seg_b200.engine.UNetEvalPlan; slot: a second plan with its own activation buffers,
         used when two window groups run concurrently on two streams)."""
-        from vs_seg_b200.engine import UNetEvalPlan
+        from vs_seg_b200.engine import UNetEvalPlan, batch_first_enabled
         if not self._plan_supported():
             raise NotImplementedError("the native plan covers the reference configuration "
                                       "(3-D, num_res_units=2, BatchNorm, PReLU, 1 input channel)")
         device = torch.device(device) if device is not None else next(self.parameters()).device
-        key = (tuple(int(v) for v in patch_size), int(batch), str(device), int(window_levels), int(slot))
+        key = (tuple(int(v) for v in patch_size), int(batch), str(device), int(window_levels), int(slot),
+               batch_first_enabled())
         ver = self._weights_version()
         hit = self._plans.get(key)
         if hit is None or hit[0] != ver:

@@ -31,3 +31,27 @@ def test_bad_arguments_return_einval_without_gpu():
     code = h.vsseg_sw_finalize(None, None, None, 2, 10, None, None, 0, None, None)
     assert code == 100001
     assert b"sw_finalize" in h.vsseg_last_error()
+
+
+def test_inconsistent_window_set_is_rejected_without_gpu():
+    """vsseg_f32view.n_windows: a window set must hold out->B single-window records of one volume; everything that
+    does not take window sets rejects them (validated before any launch, so no GPU is needed)."""
+    import ctypes as C
+    h = lib.load()
+    n = 8 * 8 * 8
+    views = (lib.F32View * 2)()
+    for i in range(2):
+        views[i] = lib.F32View(4096 + 64 * i, n, n, 64, 8, 1, 1, 1, 8, 8, 8, 0, None)
+    out = lib.Act8(4096, 2 * 16 * n, 16 * n, 2, 16, 8, 8, 8)
+    g = lib.ConvGeom(3, 3, 1, 1, 1, 1, 0)
+    ep = lib.Epilogue(4096, 4096, 0.25, 0)
+    views[0].n_windows = 3                      # three records announced for a batch of two
+    assert h.vsseg_conv3d_cin1(views, C.byref(out), C.byref(g), 4096, C.byref(ep), None) == 100001
+    assert b"shape mismatch" in h.vsseg_last_error()
+    views[0].n_windows = 2
+    views[1].sy = 16                            # the records do not describe windows of one volume
+    assert h.vsseg_conv3d_cin1(views, C.byref(out), C.byref(g), 4096, C.byref(ep), None) == 100001
+    assert b"window set" in h.vsseg_last_error()
+    views[1].sy = 8
+    att = lib.Act8(4096, 2 * 8 * n, 8 * n, 2, 8, 8, 8, 8)
+    assert h.vsseg_att_gate(C.byref(att), views, C.byref(att), None) == 100001   # plain views only

@@ -108,6 +108,37 @@ def test_window_group_plan_equals_single_window_plan_at_128():
     assert not any(st.name.endswith(".gate") and st.name.startswith("dec0") for st in grp.steps)   # no top-level gate pass
 
 
+@pytest.mark.parametrize("roi,vol_shape,starts", [
+    ((128, 128, 128), (1, 1, 224, 128, 160), [(0, 0, 0), (96, 0, 32), (48, 0, 16)]),
+    ((64, 64, 16), (2, 1, 96, 80, 24), [(0, 0, 0), (32, 16, 8), (16, 0, 4), (8, 16, 0), (24, 8, 8)]),
+])
+def test_batch_first_window_set_equals_per_window_launches(monkeypatch, roi, vol_shape, starts):
+    """VSSEG_SW_BATCH_FIRST=1: the first ResidualUnit of every window in one launch per conv (the windows' source views
+    travel as a window set, vsseg_f32view.n_windows) == one launch per window, bit for bit; the second case takes its
+    windows from two batch entries of the volume."""
+    from vs_seg_b200.tensors import f32view
+    net = _native_net(unet_oracle.seeded_state_dict(0))
+    vol = torch.randn(vol_shape, generator=torch.Generator().manual_seed(5)).to(_dev())
+    imap = torch.rand(roi, generator=torch.Generator().manual_seed(6)).to(_dev())
+    nb = vol_shape[0]
+    accs = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("VSSEG_SW_BATCH_FIRST", mode)
+        grp = net.eval_plan(roi, batch=len(starts), window_levels=1)
+        names = [st.name for st in grp.steps]
+        assert ("enc0.unit1" in names) == (mode == "1") and ("enc0.unit1@w0" in names) == (mode == "0")
+        acc = torch.zeros((nb, 2) + tuple(vol_shape[2:]), device=_dev())
+        srcs = [f32view(vol[i % nb:i % nb + 1], s_, roi) for i, s_ in enumerate(starts)]
+        dsts = [f32view(acc[i % nb:i % nb + 1], s_, roi) for i, s_ in enumerate(starts)]
+        for _ in range(2):   # the second run re-binds the same records
+            acc.zero_()
+            grp.run(srcs, dsts, imap.data_ptr())
+        torch.cuda.synchronize()
+        accs.append(acc)
+    assert torch.equal(accs[0], accs[1])
+    assert accs[0].abs().max().item() > 0
+
+
 def test_unet_eval_128_matches_oracle():
     """Whole-network eval forward at 128^3 (the benchmark window) vs the CPU oracle: logits and attention maps."""
     sd = unet_oracle.seeded_state_dict(0)

@@ -81,8 +81,37 @@ __device__ __forceinline__ float* f32_base(const vsseg_f32view& v) {
         return reinterpret_cast<float*>(__ldg(reinterpret_cast<const long long*>(v.indirect)) + reinterpret_cast<long long>(v.ptr));
     return v.ptr;
 }
-inline bool f32_ok(const vsseg_f32view* v) { return v && (v->ptr || v->indirect); }
-inline bool f32_direct(const vsseg_f32view* v) { return v && v->ptr && !v->indirect; }
+inline bool f32_set_ok(const vsseg_f32view* v) { return v && (v->ptr || v->indirect); }            // plain view or window set
+inline bool f32_ok(const vsseg_f32view* v) { return f32_set_ok(v) && v->n_windows <= 1; }         // plain view
+inline bool f32_direct(const vsseg_f32view* v) { return f32_ok(v) && v->ptr && !v->indirect; }
+
+// Window set (vsseg_f32view.n_windows > 1, include/vsseg_b200.h): batch item b of the view is the window described by
+// record b.  The kernels keep record 0 and this table of element offsets of the other windows from it.
+struct WinTab {
+    int32_t n;                            // 0: plain view, batch item b at b * sb
+    int64_t off[VSSEG_MAX_WINDOWS];
+};
+// fills `t` from the records behind `v`; false when they do not form a window set of `batch` items
+inline bool win_tab(const vsseg_f32view* v, int batch, WinTab* t) {
+    t->n = 0;
+    for (int i = 0; i < VSSEG_MAX_WINDOWS; ++i) t->off[i] = 0;
+    if (!v || v->n_windows <= 1) return true;
+    if (v->n_windows != batch || batch > VSSEG_MAX_WINDOWS) return false;
+    for (int i = 0; i < batch; ++i) {
+        const vsseg_f32view& r = v[i];
+        if (r.B != 1 || r.C != v->C || r.X != v->X || r.Y != v->Y || r.Z != v->Z || r.sc != v->sc || r.sx != v->sx ||
+            r.sy != v->sy || r.sz != v->sz || r.indirect != v->indirect || !f32_set_ok(&r))
+            return false;
+        const long long d = (long long)(reinterpret_cast<intptr_t>(r.ptr) - reinterpret_cast<intptr_t>(v->ptr));
+        if (d % (long long)sizeof(float)) return false;
+        t->off[i] = d / (long long)sizeof(float);
+    }
+    t->n = batch;
+    return true;
+}
+__device__ __forceinline__ int64_t win_off(const vsseg_f32view& v, const WinTab& t, int b) {
+    return t.n ? t.off[b] : (int64_t)b * v.sb;
+}
 
 // element offset of (b, cg, x, y, z) group start in an act8 plane
 __device__ __forceinline__ int64_t act8_off(int64_t bstride, int X, int Y, int Z, int b, int cg, int x, int y, int z) {

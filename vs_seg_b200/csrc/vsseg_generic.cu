@@ -226,6 +226,7 @@ struct Cin1Args {
     vsseg_conv_geom g;
     const float* w;  // [taps][Cout]
     vsseg_epilogue ep;
+    WinTab win;      // `in` is a window set: batch item b is read at win.off[b]
 };
 
 template <int COUT>
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(128) conv_cin1_kernel(const Cin1Args a) {
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-    const float* src = f32_base(a.in) + (int64_t)b * a.in.sb;
+    const float* src = f32_base(a.in) + win_off(a.in, a.win, b);
     int tap = 0;
     for (int tx = 0; tx < a.g.kx; ++tx)
         for (int ty = 0; ty < a.g.ky; ++ty) {
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(128) conv_cin1_k331_kernel(const Cin1Args a) {
     for (int v = 0; v < CIN1_YB; ++v)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc2[v][c] = make_float2(0.f, 0.f);
-    const float* src = f32_base(a.in) + (int64_t)b * a.in.sb + (int64_t)z * a.in.sz;
+    const float* src = f32_base(a.in) + win_off(a.in, a.win, b) + (int64_t)z * a.in.sz;
 #pragma unroll
     for (int tx = 0; tx < 3; ++tx) {
         const int xi = x - 1 + tx;
@@ -664,13 +665,17 @@ int vsseg_conv3d_act8(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
 
 int vsseg_conv3d_cin1(const vsseg_f32view* in, const vsseg_act8* out, const vsseg_conv_geom* g, const float* w,
                       const vsseg_epilogue* ep, void* stream) {
-    VSSEG_REQUIRE(f32_ok(in) && act8_ok(out), "conv3d_cin1: bad tensor descriptor");
+    VSSEG_REQUIRE(f32_set_ok(in) && act8_ok(out), "conv3d_cin1: bad tensor descriptor");
     if (int e = check_geom(g, "conv3d_cin1")) return e;
     VSSEG_REQUIRE(g->sx == 1 && g->sy == 1 && g->sz == 1 && !g->transposed, "conv3d_cin1: stride-1 conv only");
     VSSEG_REQUIRE(out->C == 16, "conv3d_cin1: Cout must be 16 (got %d)", out->C);
-    VSSEG_REQUIRE(in->X == out->X && in->Y == out->Y && in->Z == out->Z && in->B == out->B, "conv3d_cin1: shape mismatch");
+    const bool set = in->n_windows > 1;   // every window of a sliding-window group in one launch
+    VSSEG_REQUIRE(in->X == out->X && in->Y == out->Y && in->Z == out->Z && (set ? in->n_windows : in->B) == out->B,
+                  "conv3d_cin1: shape mismatch");
     VSSEG_REQUIRE(w && ep && ep->scale && ep->shift, "conv3d_cin1: NULL weights/epilogue");
-    Cin1Args a{*in, *out, *g, w, *ep};
+    Cin1Args a{*in, *out, *g, w, *ep, {}};
+    VSSEG_REQUIRE(win_tab(in, out->B, &a.win), "conv3d_cin1: inconsistent window set (%d records for batch %d)",
+                  in->n_windows, out->B);
     const int64_t nvox = (int64_t)out->B * out->X * out->Y * out->Z;
     const unsigned nblk = (unsigned)((int64_t)out->B * out->X * out->Y * ((out->Z + 127) / 128));
     if (g->kx == 3 && g->ky == 3 && g->kz == 1 && ep->act != 1) {

@@ -64,6 +64,7 @@ struct TcArgs {
     int res_mode;            // 0 none, 1 act8 addend, 2 cin1 affine
     vsseg_act8 res;
     vsseg_f32view rsrc;
+    WinTab rwin;             // rsrc is a window set: batch item b reads its window at rwin.off[b]
     const float* res_w;
     const float* res_b;
     const float* bias2;      // shortcut bias [Cout] (segment 2)
@@ -116,6 +117,9 @@ struct TcArgs {
 };
 
 constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
+#ifndef VSSEG_GATE_BATCH
+#define VSSEG_GATE_BATCH 1   // fused attention gate (out mode 2): channel groups loaded ahead of the first store (experiment knob)
+#endif
 #ifndef VSSEG_TC_EPI_WARPS
 #define VSSEG_TC_EPI_WARPS 16
 #endif
@@ -172,7 +176,7 @@ struct EpiCtx {
     int b, ox, my0, mz0, ly, zz, co0, nreal;
     bool sc, sig;
     float slope;
-    const float* rsrc_p;   // base pointers of the fp32 views (relocatable views resolved once per thread)
+    const float* rsrc_p;   // base pointers of the fp32 views (relocatable views resolved once per thread); rsrc_p: of batch item b
     float* outf_p;
 };
 template <bool SC, int RM>
@@ -215,7 +219,7 @@ __device__ __forceinline__ void epi_load(const EpiCtx& X, EpiUnit<SC, RM>& U) {
         }
       }
     } else if constexpr (RM == 2) {
-        if (U.valid) U.rsrc = __ldg(X.rsrc_p + X.b * a.rsrc.sb + X.ox * a.rsrc.sx + U.oy * a.rsrc.sy + U.oz * a.rsrc.sz);
+        if (U.valid) U.rsrc = __ldg(X.rsrc_p + X.ox * a.rsrc.sx + U.oy * a.rsrc.sy + U.oz * a.rsrc.sz);
     }
 }
 
@@ -251,8 +255,32 @@ __device__ __forceinline__ void epi_finish(const EpiCtx& X, EpiUnit<SC, RM>& U) 
                     __nv_bfloat16* gp = (__nv_bfloat16*)a.gate.hi + (int64_t)X.b * a.gate.batch_stride +
                                         (((int64_t)X.ox * Yg + U.oy) * Zg + U.oz) * 8;
                     const int ncg = a.gate.C >> 3;
+                    int cg = 0;
+#if VSSEG_GATE_BATCH > 1
+                    // the loads of VSSEG_GATE_BATCH channel groups are issued before the first store (the compiler cannot
+                    // move a load above a store through the same pointer): 2 x VSSEG_GATE_BATCH 128-bit loads in flight
+                    for (; cg + VSSEG_GATE_BATCH <= ncg; cg += VSSEG_GATE_BATCH, gp += VSSEG_GATE_BATCH * cgs_g) {
+                        uint4 hh[VSSEG_GATE_BATCH], ll[VSSEG_GATE_BATCH];
+#pragma unroll
+                        for (int j = 0; j < VSSEG_GATE_BATCH; ++j) {
+                            hh[j] = ldg128_plain(gp + j * cgs_g);
+                            ll[j] = ldg128_plain(gp + j * cgs_g + a.gate.lo_offset);
+                        }
+#pragma unroll
+                        for (int j = 0; j < VSSEG_GATE_BATCH; ++j) {
+                            float xv[8];
+                            unpack8(hh[j], ll[j], xv);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) xv[k] *= gsc;
+                            uint4 h, l;
+                            pack8(xv, h, l);
+                            *reinterpret_cast<uint4*>(gp + j * cgs_g) = h;
+                            *reinterpret_cast<uint4*>(gp + j * cgs_g + a.gate.lo_offset) = l;
+                        }
+                    }
+#endif
 #pragma unroll 2
-                    for (int cg = 0; cg < ncg; ++cg, gp += cgs_g) {
+                    for (; cg < ncg; ++cg, gp += cgs_g) {
                         float xv[8];
                         unpack8(ldg128_plain(gp), ldg128_plain(gp + a.gate.lo_offset), xv);
 #pragma unroll
@@ -691,6 +719,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             const int64_t tile_off = ((int64_t)(my0 * a.uy) * Zo + mz0 * a.uz) * 8 + thr_off + (int64_t)(co0 >> 3) * cgs;
             __nv_bfloat16* const out_b = (__nv_bfloat16*)a.out.hi + (int64_t)b * a.out.batch_stride;
             const __nv_bfloat16* const res_b = (const __nv_bfloat16*)a.res.hi + (int64_t)b * a.res.batch_stride;
+            const float* const rsrc_b = RM == 2 ? rsrc_p + win_off(a.rsrc, a.rwin, b) : nullptr;   // window b of a window set
             for (int r = 0; r < T.xt; ++r) {
                 const int g = rowbase + r, slot = g % R;
                 const uint32_t tacc = tlane + (uint32_t)slot * slot_cols;
@@ -702,7 +731,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 if (a.dbg) t_wait += clock64() - t0;
                 // units = (accumulator ai, 16-column chunk c), dealt to the quadrant's warps like the zeroing below
                 // (two units in flight per thread were tried: the extra registers spill and it is slower)
-                EpiCtx X{a, ep_c, tacc, row_cols, row_off, cgs, lo_out, lo_res, out_b, res_b, b, ox, my0, mz0, ly, zz, co0, nreal, sc, sig, slope, rsrc_p, outf_p};
+                EpiCtx X{a, ep_c, tacc, row_cols, row_off, cgs, lo_out, lo_res, out_b, res_b, b, ox, my0, mz0, ly, zz, co0, nreal, sc, sig, slope, rsrc_b, outf_p};
                 int ai = 0, c = esub;
                 while (c >= n16) { c -= n16; ++ai; }
                 while (ai < a.nacc) {
@@ -1401,9 +1430,11 @@ int vsseg_conv3d_tc(const vsseg_act8* in, const vsseg_act8* out, const vsseg_con
         a.res_mode = 1;
         a.res = *res_act8;
     } else if (res_src) {
-        VSSEG_REQUIRE(f32_ok(res_src) && res_w && res_b, "conv3d_tc: NULL cin1 residual");
+        VSSEG_REQUIRE(f32_set_ok(res_src) && res_w && res_b, "conv3d_tc: NULL cin1 residual");
         a.res_mode = 2;
         a.rsrc = *res_src; a.res_w = res_w; a.res_b = res_b;
+        VSSEG_REQUIRE(win_tab(res_src, out->B, &a.rwin), "conv3d_tc: inconsistent window set (%d records for batch %d)",
+                      res_src->n_windows, out->B);
     }
     CUtensorMap tmap, tmap2;
     if (a.line_mode) {  // staged with plain bulk copies: no tensor map needed

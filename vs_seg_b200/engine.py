@@ -151,6 +151,12 @@ def _conv_cost(src, dst, k, transposed, cin, cout, extra_elems=0):
     return 2 * macs, nbytes
 
 
+def batch_first_enabled():
+    """VSSEG_SW_BATCH_FIRST: window-group plans run the first ResidualUnit of all windows in one launch per conv
+    (window set of source views) instead of one launch per window."""
+    return os.environ.get("VSSEG_SW_BATCH_FIRST", "0") == "1"
+
+
 class UNetEvalPlan:
     """Flat launch list for one patch shape [B,1,X,Y,Z] (X,Y % 32 == 0, Z % 8 == 0).
 
@@ -194,8 +200,12 @@ class UNetEvalPlan:
         # per window when the fine levels run per window
         self.window_levels = max(0, min(int(window_levels), len(channels) - 1)) if self.B > 1 else 0
         nview = self.B if self.window_levels else 1
-        self.srcs = [_lib.F32View() for _ in range(nview)]
-        self._dst_arr = (_lib.F32View * nview)()   # contiguous: one launch can take every window's destination
+        # contiguous records: one launch can take every window's source (a window set, vsseg_f32view.n_windows) /
+        # destination
+        self._src_arr = (_lib.F32View * nview)()
+        self.srcs = [self._src_arr[i] for i in range(nview)]
+        self._src_set = False   # the first ResidualUnit reads all windows in one launch (set by _build)
+        self._dst_arr = (_lib.F32View * nview)()
         self.dsts = [self._dst_arr[i] for i in range(nview)]
         self.src, self.dst = self.srcs[0], self.dsts[0]
         self._bs = (0, self.B)   # batch slice the step being emitted works on
@@ -331,6 +341,14 @@ class UNetEvalPlan:
                                 (C.byref(src), C.byref(out_view), C.byref(g), wg.data_ptr(), b.data_ptr(), act_code,
                                  slope, sw_weight), fl, nb))
         return False
+
+    def _batch_first_ok(self, hbuf, catbuf, c0):
+        if not batch_first_enabled() or self.B > _lib.MAX_WINDOWS or not self.use_tc:
+            return False
+        # the Cin=1 shortcut of unit1 takes a window set on the tensor-core path only
+        g = self._geom(self.kernel_sizes[0])
+        h, e = hbuf.view(), catbuf.view(0, c0)
+        return bool(self.lib.vsseg_conv3d_tc_supported(C.byref(h), C.byref(e), C.byref(g), 1, None))
 
     def _gate_logits_ok(self, buf, k):
         return (os.environ.get("VSSEG_GATE_LOGITS", "1") != "0" and buf.C == 32 and tuple(k) == (3, 3, 1)
@@ -512,10 +530,18 @@ class UNetEvalPlan:
         # (first ResidualUnit, logits conv); the rest of the finest level is batched like the coarse ones
         split0 = d == 1
         # ---- fine levels of the encoder, window by window
-        for bs in windows:
-            self._bs = bs
-            for l in range(d):
-                encoder(l, "units" if split0 else "all")
+        # VSSEG_SW_BATCH_FIRST=1: the first ResidualUnit of every window in ONE launch per conv - the windows' source
+        # views travel as a window set (include/vsseg_b200.h).  A single 128^3 window is 128-144 tiles for 148
+        # persistent CTAs (one tile each: the pipeline ramp is never amortised); the group is 1024 tiles.
+        self._src_set = bool(split0 and self._batch_first_ok(hb[0], cat[0], ch[0]))
+        if self._src_set:
+            self._bs = (0, self.B)
+            encoder(0, "units")
+        else:
+            for bs in windows:
+                self._bs = bs
+                for l in range(d):
+                    encoder(l, "units" if split0 else "all")
         # ---- coarse levels, all windows at once
         self._bs = (0, self.B)
         if split0:
@@ -562,6 +588,10 @@ class UNetEvalPlan:
                 raise ValueError("run(): view shapes do not match the plan")
         for mine, new in zip(self.srcs + self.dsts, srcs + dsts):
             self._set(mine, new)
+        if self._src_set:   # record 0 heads the window set of all B sources
+            if any(s_.n_windows > 1 for s_ in srcs):
+                raise ValueError("run(): source views must be plain single-window views")
+            self._src_arr[0].n_windows = self.B
         self.sw_weight.value = sw_weight_ptr
         if atomic and self._has_plain_blend:
             raise _lib.NativeLibraryError("this plan blends with a launch that has no atomic mode")

@@ -26,7 +26,10 @@ class F32View(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sb", C.c_int64), ("sc", C.c_int64), ("sx", C.c_int64),
                 ("sy", C.c_int64), ("sz", C.c_int64),
                 ("B", C.c_int32), ("C", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32),
-                ("reserved", C.c_int32), ("indirect", C.c_void_p)]   # indirect: device cell holding the base address
+                ("n_windows", C.c_int32), ("indirect", C.c_void_p)]   # indirect: device cell holding the base address
+
+
+MAX_WINDOWS = 16   # VSSEG_MAX_WINDOWS: records of a window set (F32View.n_windows, include/vsseg_b200.h)
 
 
 class Epilogue(C.Structure):

@@ -26,6 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from . import lib as _lib
+from .engine import batch_first_enabled
 from .tensors import f32view
 
 _IMAP_CACHE: dict = {}
@@ -289,7 +290,8 @@ def _program(model, inputs, roi_size, jobs, imap, image_size, extra, peer=False)
     """Cached _Program for (model weights, volume layout, geometry, shard)."""
     key = (id(model), model._weights_version(), tuple(inputs.shape), tuple(inputs.stride()), str(inputs.device),
            tuple(roi_size), extra, os.environ.get("VSSEG_SW_GROUP", "8"), os.environ.get("VSSEG_SW_WINDOW_LEVELS", "1"),
-           os.environ.get("VSSEG_SW_GRAPH", "1"), os.environ.get("VSSEG_SW_STREAMS", "2"), bool(peer))
+           os.environ.get("VSSEG_SW_GRAPH", "1"), os.environ.get("VSSEG_SW_STREAMS", "2"), bool(peer),
+           batch_first_enabled())
     prog = _PROGRAMS.get(key)
     if prog is None:
         if len(_PROGRAMS) >= 3:   # each program owns an accumulator volume and a captured graph
