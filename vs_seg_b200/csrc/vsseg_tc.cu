@@ -118,7 +118,7 @@ struct TcArgs {
 
 constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
 #ifndef VSSEG_GATE_BATCH
-#define VSSEG_GATE_BATCH 1   // fused attention gate (out mode 2): channel groups loaded ahead of the first store (experiment knob)
+#define VSSEG_GATE_BATCH 4   // fused attention gate (out mode 2): channel groups loaded ahead of the first store (measured: 1 -> 4: dec3 0.119 -> 0.080, dec2 0.222 -> 0.198 ms per group of 8 windows; 8 spills and is slower)
 #endif
 #ifndef VSSEG_TC_EPI_WARPS
 #define VSSEG_TC_EPI_WARPS 16
@@ -875,6 +875,19 @@ static bool gen_ops(const TcGeom& G, int YT, TcOp* ops, int* nop_out, TcAcc* acc
     return true;
 }
 
+// Measured tile choices (tools/autotune_tiles.py on a B200: every launch of a group of 8 windows of 128^3 re-timed with
+// every feasible (XT, YT)) for the layers where the cost model below misses the fastest tile by more than the ~3 %
+// run-to-run noise of the sweep (profiles/r02_autotune_tiles.tsv).  Keyed by the layer's geometry; anything else,
+// and batches of fewer than 4 windows, goes through the cost model.
+struct TileHint { int cin, cout_pad, Xm, Ym, Zm, k, s, tr, sc, xt, yt; };   // k, s: kx ky kz / sx sy sz as decimal digits
+static const TileHint kTileHints[] = {
+    {64, 32, 64, 64, 128, 331, 111, 0, 1, 1, 8},    // dec1.unit0 (+ fused shortcut): 0.770 -> 0.702 ms
+    {32, 32, 64, 64, 128, 331, 111, 0, 1, 1, 4},    // enc1.unit1 (+ fused shortcut): 0.399 -> 0.384 ms
+    {64, 48, 16, 16, 64, 333, 222, 1, 0, 1, 1},     // up2 (transposed): 0.139 -> 0.113 ms
+    {80, 64, 8, 8, 32, 333, 222, 1, 0, 1, 1},       // up3 (transposed): 0.034 -> 0.031 ms
+    {64, 16, 16, 16, 64, 333, 111, 0, 0, 2, 2},     // dec3.att.conv2 (+ fused gate): 0.112 -> 0.080 ms
+};
+
 // Fills the plan for (in -> out, geometry, n_split); returns false when the shape is not covered
 // (the caller then uses the generic CUDA-core kernel).
 static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, const vsseg_conv_geom* g, int n_split,
@@ -958,8 +971,24 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     static const int ts_env = getenv("VSSEG_TC_TS") ? atoi(getenv("VSSEG_TC_TS")) : 0;
     const bool ts_ok = ts_env != 0 && !tr && !strided && !line && KZ == 1 && LY == 1;
     const int sms_ = sm_count();
+    // VSSEG_TC_FORCE="XT,YT[,nstage]" (tools/autotune_tiles.py): only that tile is considered; read on every call
+    int f_xt = 0, f_yt = 0, f_nst = 0;
+    static const bool use_hints = !(getenv("VSSEG_TC_HINTS") && atoi(getenv("VSSEG_TC_HINTS")) == 0);
+    bool hinted = false;
+    if (const char* f = getenv("VSSEG_TC_FORCE")) {
+        sscanf(f, "%d,%d,%d", &f_xt, &f_yt, &f_nst);
+    } else if (use_hints && in->B >= 4) {
+        const int kk = KX * 100 + KY * 10 + KZ, ss = g->sx * 100 + g->sy * 10 + g->sz;
+        for (const TileHint& h : kTileHints)
+            if (h.cin == in->C && h.cout_pad == cout_pad && h.Xm == Xm && h.Ym == Ym && h.Zm == Zm && h.k == kk && h.s == ss &&
+                h.tr == (tr ? 1 : 0) && h.sc == (src2 ? 1 : 0) && n_split == 1) {
+                f_xt = h.xt; f_yt = h.yt; hinted = true;
+            }
+    }
+search:
     for (int ts = 0; ts <= (ts_ok ? 1 : 0); ++ts)
     for (int XT = 1; XT <= (xt_ok ? (xt_max < Xm ? xt_max : Xm) : 1); ++XT) {
+        if (f_xt && XT != f_xt) continue;
         if (XT > 1 && XT < xt_min && xt_min <= Xm) continue;
         const int nseg = (Xm + XT - 1) / XT;
         if (XT > 1 && (Xm + nseg - 1) / nseg != XT) continue;   // keep the segments balanced
@@ -967,6 +996,7 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
         const long total_tiles_1 = (long)in->B * nseg * (Zm / LZ) * (tr ? 2 : 1) * n_split;
         for (int YT = 1; YT <= ygroups && YT <= yt_max; ++YT) {
             if (ygroups % YT) continue;
+            if (f_yt && YT != f_yt) continue;
             const int cols1 = YT * acc_mult * n_cta;   // TMEM columns of one row slot
             if (cols1 > 512) break;
             if (YT * acc_mult > TC_MAX_ACC) break;
@@ -1042,9 +1072,15 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
             if (cost < best_cost || (ts_env == 2 && ts && !best_ts)) {
                 best_cost = cost; best = YT; best_xt = XT; best_stage = stage; best_slots = slots;
                 best_nstage = nst > nstage_max ? nstage_max : nst;
+                if (f_nst >= 2 && f_nst < best_nstage) best_nstage = f_nst;
                 best_ts = ts != 0;
             }
         }
+    }
+    if (!best && hinted) {   // the hinted tile does not fit this variant of the layer: let the cost model choose
+        hinted = false;
+        f_xt = f_yt = 0;
+        goto search;
     }
     if (!best) return false;
     const int YT = best, XT = best_xt;
@@ -1185,6 +1221,11 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     k.v[21] = src2 ? 1 : 0;
     k.v[22] = g->kx | (g->ky << 4) | (g->kz << 8) | (g->sx << 12) | (g->sy << 16) | (g->sz << 20) | ((g->transposed ? 1 : 0) << 24);
     k.v[23] = n_split;
+    if (const char* f = getenv("VSSEG_TC_FORCE")) {   // forced tiles are separate cache entries
+        int fx = 0, fy = 0, fn = 0;
+        sscanf(f, "%d,%d,%d", &fx, &fy, &fn);
+        k.v[24] = fx; k.v[25] = fy * 16 + fn;
+    }
     struct Entry { TcKey k; bool ok; TcPlan p; };
     static std::vector<Entry>* cache = new std::vector<Entry>();
     for (const Entry& e : *cache)

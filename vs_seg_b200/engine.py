@@ -154,7 +154,7 @@ def _conv_cost(src, dst, k, transposed, cin, cout, extra_elems=0):
 def batch_first_enabled():
     """VSSEG_SW_BATCH_FIRST: window-group plans run the first ResidualUnit of all windows in one launch per conv
     (window set of source views) instead of one launch per window."""
-    return os.environ.get("VSSEG_SW_BATCH_FIRST", "0") == "1"
+    return os.environ.get("VSSEG_SW_BATCH_FIRST", "1") == "1"
 
 
 class UNetEvalPlan:
@@ -319,11 +319,12 @@ class UNetEvalPlan:
                 shift = self._dev(torch.nn.functional.pad(bias.float(), (0, 16 - cout)))
                 ep = _lib.Epilogue(scale.data_ptr(), shift.data_ptr(), slope, act_code)
                 self._keep.append(ep)
-                # measured (group of 8 windows): the fused gate wins where the gated tensor is small enough for its
-                # traffic to hide behind the MMAs (level 3 and coarser: -9 us per window at 32x32x128); on the two
-                # finest levels the gate is the larger half and runs faster as its own bandwidth-bound launch
+                # measured (group of 8 windows): with the loads of four channel groups in flight ahead of the first
+                # store the fused gate wins down to 64x64x128 (conv2 + gate 0.160 + 0.383 ms -> 0.488 ms fused; level 3:
+                # -9 us per window); at 128^3 the gate is applied on the fly by the gate+logits launch, and when that is
+                # off it runs faster as its own bandwidth-bound launch
                 fuse_env = os.environ.get("VSSEG_FUSE_GATE", "auto")
-                fuse = fuse_env == "1" or (fuse_env == "auto" and gate is not None and _nvox(gate) // gate.B <= 32 * 32 * 128)
+                fuse = fuse_env == "1" or (fuse_env == "auto" and gate is not None and _nvox(gate) // gate.B <= 64 * 64 * 128)
                 if gate is not None and cout == 1 and sw_weight is None and fuse:
                     self._keep.append(gate)
                     self.steps.append(_Step(name + "+gate", self.lib.vsseg_conv3d_tc_attgate,
