@@ -132,24 +132,25 @@ class UNet2d5_spvPA(nn.Module):
         return (self.dimensions == 3 and self.num_res_units == 2 and str(name).upper() == "BATCH"
                 and str(act).upper() == "PRELU" and self.in_channels == 1 and self.out_channels in (1, 2))
 
-    def eval_plan(self, patch_size, batch=1, device=None, window_levels=0, slot=0):
+    def eval_plan(self, patch_size, batch=1, device=None, window_levels=0, slot=0, atomic_out=False):
         """The cached fused launch plan for eval-mode inference on [batch,1,*patch_size]
         (window_levels: see vs_seg_b200.engine.UNetEvalPlan; slot: a second plan with its own activation buffers,
-        used when two window groups run concurrently on two streams)."""
+        used when two window groups run concurrently on two streams; atomic_out: the caller blends with atomics, so
+        the last launch takes all windows of the group at once)."""
         from vs_seg_b200.engine import UNetEvalPlan, batch_first_enabled
         if not self._plan_supported():
             raise NotImplementedError("the native plan covers the reference configuration "
                                       "(3-D, num_res_units=2, BatchNorm, PReLU, 1 input channel)")
         device = torch.device(device) if device is not None else next(self.parameters()).device
         key = (tuple(int(v) for v in patch_size), int(batch), str(device), int(window_levels), int(slot),
-               batch_first_enabled())
+               batch_first_enabled(), bool(atomic_out))
         ver = self._weights_version()
         hit = self._plans.get(key)
         if hit is None or hit[0] != ver:
             if len(self._plans) >= 8:
                 self._plans.clear()
             plan = UNetEvalPlan(self.state_dict(), key[0], batch=batch, device=device, attention=self.attention_module,
-                                window_levels=window_levels,
+                                window_levels=window_levels, atomic_out=atomic_out,
                                 channels=self.channels, strides=self.strides, kernel_sizes=self.kernel_sizes,
                                 sample_kernel_sizes=self.sample_kernel_sizes, in_channels=self.in_channels,
                                 out_channels=self.out_channels)

@@ -325,6 +325,35 @@ def test_tcgen05_fused_shortcut(B, cin, csrc, cout, dims, k):
     assert err < 5e-5 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("B,cin,cout,dims,k", [
+    (2, 64, 32, (20, 16, 128), (3, 3, 1)),    # dec1.unit0 flavour: x march (or the hinted 8-line tile), box mode
+    (4, 64, 32, (64, 64, 128), (3, 3, 1)),    # ... at the geometry of the measured tile hint (B >= 4)
+    (1, 96, 48, (6, 8, 128), (3, 3, 3)),      # dec2.unit0 flavour: line mode, z halo
+    (2, 128, 64, (6, 8, 64), (3, 3, 3)),      # dec3.unit0 flavour: three z boxes per stage, the centre one is the shortcut's
+    (1, 160, 80, (8, 8, 32), (3, 3, 3)),      # dec4.unit0 flavour
+    (1, 32, 32, (5, 8, 16), (1, 1, 1)),       # no x taps at all
+])
+def test_tcgen05_shortcut_of_the_conv_input(B, cin, cout, dims, k):
+    """Decoder ResidualUnit (one subunit, convolutions.py:241-255): the 1x1x1 shortcut reads the conv's own input, so
+    its MMAs ride on the centre-tap stages of the conv (no shortcut stages)."""
+    from vs_seg_b200.engine import conv_block_ncdhw
+    dev = _dev()
+    blk = _seeded_block(cin, cout, k, (1, 1, 1), False, 2 * cin + cout)
+    sc = torch.nn.Conv3d(cin, cout, 1)
+    x = torch.randn(B, cin, *dims, generator=torch.Generator().manual_seed(cin + dims[0]))
+    with torch.no_grad():
+        ref = blk(x) + sc(x)
+        sd = {"conv." + n: v for n, v in blk.conv.state_dict().items()}
+        sd.update({"norm." + n: v for n, v in blk.norm.state_dict().items()})
+        sd["act.weight"] = blk.act.weight
+        sd = {n: v.to(dev) for n, v in sd.items()}
+        xd = x.to(dev)
+        got = conv_block_ncdhw(xd, sd, k, (1, 1, 1), False, True, "prelu",
+                               shortcut=(xd, sc.weight.detach().to(dev), sc.bias.detach().to(dev)), require_tc=True).cpu()
+    err = (got - ref).abs().max().item()
+    assert err < 5e-5 * max(1.0, ref.abs().max().item()), err
+
+
 # ---- Dice_spvPA loss: native kernels vs the oracle (values and gradients) ---------------------------
 def _loss_inputs(B, dims, seed, empty=False, full=False):
     g = torch.Generator().manual_seed(seed)

@@ -139,6 +139,31 @@ def test_batch_first_window_set_equals_per_window_launches(monkeypatch, roi, vol
     assert accs[0].abs().max().item() > 0
 
 
+def test_atomic_out_plan_takes_all_windows_in_one_launch():
+    """Plans built for an accumulator that several writers share (multi-GPU peer blend, vs_seg_b200/peer.py) blend
+    every window of the group in ONE gate+logits launch with red.global.add; the sum order of overlapping windows is
+    unspecified, so the result agrees with the per-window launches to fp32 rounding."""
+    from vs_seg_b200.tensors import f32view
+    net = _native_net(unet_oracle.seeded_state_dict(0))
+    roi = (64, 64, 16)
+    vol = torch.randn((1, 1, 96, 80, 24), generator=torch.Generator().manual_seed(8)).to(_dev())
+    starts = [(0, 0, 0), (32, 16, 8), (16, 0, 4), (8, 16, 0)]
+    imap = torch.rand(roi, generator=torch.Generator().manual_seed(9)).to(_dev())
+    ref_plan = net.eval_plan(roi, batch=len(starts), window_levels=1)
+    at_plan = net.eval_plan(roi, batch=len(starts), window_levels=1, atomic_out=True)
+    assert sum(st.name.startswith("dec0.gate+logits") for st in at_plan.steps) == 1
+    assert sum(st.name.startswith("dec0.gate+logits") for st in ref_plan.steps) == len(starts)
+    acc1 = torch.zeros((1, 2, 96, 80, 24), device=_dev())
+    acc2 = torch.zeros_like(acc1)
+    srcs = [f32view(vol, s_, roi) for s_ in starts]
+    ref_plan.run(srcs, [f32view(acc1, s_, roi) for s_ in starts], imap.data_ptr())
+    at_plan.run(srcs, [f32view(acc2, s_, roi) for s_ in starts], imap.data_ptr(), atomic=True)
+    torch.cuda.synchronize()
+    assert (acc1 - acc2).abs().max().item() <= 1e-5 * max(1.0, acc1.abs().max().item())
+    with pytest.raises(ValueError):
+        at_plan.run(srcs, [f32view(acc2, s_, roi) for s_ in starts], imap.data_ptr())
+
+
 def test_unet_eval_128_matches_oracle():
     """Whole-network eval forward at 128^3 (the benchmark window) vs the CPU oracle: logits and attention maps."""
     sd = unet_oracle.seeded_state_dict(0)

@@ -114,6 +114,14 @@ struct TcArgs {
     uint32_t a_tmem_col;       // first TMEM column of the A buffers
     uint32_t a_cols;           // columns of one A buffer: BY views x 2 planes x 8
     int na;                    // A buffers
+    // The shortcut reads the SAME tensor as the conv (decoder ResidualUnits): no shortcut stages - the stage of the
+    // centre x tap of a row already holds the shortcut's A views (centre y/z tap); it also carries the shortcut weights
+    // of its channel chunk at b2_off and the row's issuer adds the shortcut MMAs to it
+    int sc_self;
+    uint32_t b2_off;
+    // programmatic dependent launch (VSSEG_TC_PDL): the kernel lets its successor's CTAs become resident as SMs free up
+    // and itself waits for its predecessor only after its own set-up (barriers, tensor memory, epilogue constants)
+    int pdl;
 };
 
 constexpr int TC_HDR = 1024 + 5 * 1024;  // barriers + epilogue constants
@@ -382,6 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     float* ep_c = reinterpret_cast<float*>(smem + 1024);
     const uint32_t ring = smem_u32(smem) + TC_HDR;
 
+    if (a.pdl) asm volatile("griddepcontrol.launch_dependents;");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row_cols = (uint32_t)(a.nacc * a.n_cta);
     const uint32_t slot_cols = row_cols * (a.nchunk2 ? 2 : 1);
@@ -429,6 +438,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above touched only constants of the plan (weights and epilogue tables are never written by a launch);
+    // from here on the kernel reads what its predecessor wrote
+    if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0 && a.line_mode) {
         // ===== bulk-copy producer: every lane issues whole z lines (2 KB contiguous in act8) =====
@@ -438,7 +450,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             const TcTile T = decode_tile(a, tile);
             for (int q = T.q_lo; q <= T.q_hi; ++q) {
                 const int rs = q - jc;
-                const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                const int n2 = (a.nchunk2 && !a.sc_self && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
                 for (int cs = 0; cs < a.nchunk + n2; ++cs) {
                     const bool seg2 = cs >= a.nchunk;
                     const int c = seg2 ? cs - a.nchunk : cs;
@@ -461,10 +473,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     if (lane == 0) {
                         // XT > 1: the plane feeds all x taps, so the stage carries the weights of every tap
                         const uint32_t bb = seg2 ? a.b2_bytes : (a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes);
-                        mbar_expect_tx(full + st, (uint32_t)ncopy * (row_bytes + (zl ? 16u : 0u) + (zh ? 16u : 0u)) + bb);
+                        const bool sc_here = a.sc_self && rs >= 0 && rs < T.xt;   // centre x tap of row rs: + shortcut weights
+                        mbar_expect_tx(full + st, (uint32_t)ncopy * (row_bytes + (zl ? 16u : 0u) + (zh ? 16u : 0u)) + bb +
+                                                      (sc_here ? a.b2_bytes : 0u));
                         const uint8_t* wsrc = seg2 ? a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes
                                                    : a.w + ((size_t)(T.sel * a.nchunk + c) * a.nj + (a.XT > 1 ? 0 : q)) * a.b_bytes;
                         bulk_load(base + a.b_off, wsrc, bb, full + st);
+                        if (sc_here) bulk_load(base + a.b2_off, a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes, a.b2_bytes, full + st);
                     }
                     const __nv_bfloat16* g0 = (const __nv_bfloat16*)src.hi + (int64_t)T.b * src.batch_stride;
                     for (int k = lane; k < ncopy; k += 32) {
@@ -497,7 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 const TcTile T = decode_tile(a, tile);
                 for (int q = T.q_lo; q <= T.q_hi; ++q) {
                     const int rs = q - jc;
-                    const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                    const int n2 = (a.nchunk2 && !a.sc_self && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
                     for (int cs = 0; cs < a.nchunk + n2; ++cs) {
                         const bool seg2 = cs >= a.nchunk;
                         const int c = seg2 ? cs - a.nchunk : cs;
@@ -514,7 +529,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                             mbar_arrive(full + st);
                         } else if (!seg2) {
                             const uint32_t bb = a.XT > 1 ? a.nj * a.b_bytes : a.b_bytes;
-                            mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + bb);
+                            const bool sc_here = a.sc_self && rs >= 0 && rs < T.xt;   // centre x tap of row rs: + shortcut weights
+                            mbar_expect_tx(full + st, 2 * a.nbox * a.box_tx + bb + (sc_here ? a.b2_bytes : 0u));
+                            if (sc_here) bulk_load(base + a.b2_off, a.w2 + ((size_t)T.ns * a.nchunk2 + c) * a.b2_bytes, a.b2_bytes, full + st);
                             for (int i = 0; i < a.nbox; ++i) {
                                 const uint32_t dst = base + (uint32_t)a.boxes[i].dst16 * 16;
                                 const int zc = T.mz0 * a.sz + a.boxes[i].dz, yc = T.my0 * a.sy + a.boxes[i].dy;
@@ -562,7 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                         if (a.dbg) t_acc += clock64() - t0;
                     }
                     const int rs = q - jc;
-                    const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                    const int n2 = (a.nchunk2 && !a.sc_self && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
                     for (int cs = 0; cs < a.nchunk + n2; ++cs) {
                         const bool seg2 = cs >= a.nchunk;
                         const int st = it % a.nstage;
@@ -627,6 +644,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                                 mma_a<TS>(t, al, dh, bl + bp, e.idesc);
                             }
                         }
+                        if (a.sc_self && rs >= 0 && rs < T.xt && (rowbase + rs) % TC_MMA_WARPS == mw) {
+                            // this stage is the centre x tap of row rs: its centre (y, z) views are the shortcut's A operand
+                            const uint32_t ap = a.a_plane >> 4, bp = a.b2_plane >> 4;
+                            const uint32_t tr = tmem_base + (uint32_t)((rowbase + rs) % R) * slot_cols + row_cols;
+                            const uint32_t db2 = ((base + a.b2_off) & 0x3FFFF) >> 4;
+                            for (int i = 0; i < a.nop2 / 3; ++i) {
+                                const TcEl e = a.el2[i];
+                                const uint32_t al = e.a_lo + da, bl = e.b_lo + db2, t = tr + e.col;
+                                mma_a<TS>(t, al, dh, bl, e.idesc);
+                                mma_a<TS>(t, al + ap, dh, bl, e.idesc);
+                                mma_a<TS>(t, al, dh, bl + bp, e.idesc);
+                            }
+                        }
                         umma_commit(empty + st);
                         if constexpr (TS) umma_commit(a_empty + ab);
                         ++it;
@@ -655,7 +685,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 const TcTile T = decode_tile(a, tile);
                 for (int q = T.q_lo; q <= T.q_hi; ++q) {
                     const int rs = q - jc;
-                    const int n2 = (a.nchunk2 && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
+                    const int n2 = (a.nchunk2 && !a.sc_self && rs >= 0 && rs < T.xt) ? a.nchunk2 : 0;
                     for (int cs = 0; cs < a.nchunk + n2; ++cs) {
                         const bool seg2 = cs >= a.nchunk;
                         const int st = it % a.nstage, ab = it % a.na;
@@ -881,7 +911,6 @@ static bool gen_ops(const TcGeom& G, int YT, TcOp* ops, int* nop_out, TcAcc* acc
 // and batches of fewer than 4 windows, goes through the cost model.
 struct TileHint { int cin, cout_pad, Xm, Ym, Zm, k, s, tr, sc, xt, yt; };   // k, s: kx ky kz / sx sy sz as decimal digits
 static const TileHint kTileHints[] = {
-    {64, 32, 64, 64, 128, 331, 111, 0, 1, 1, 8},    // dec1.unit0 (+ fused shortcut): 0.770 -> 0.702 ms
     {32, 32, 64, 64, 128, 331, 111, 0, 1, 1, 4},    // enc1.unit1 (+ fused shortcut): 0.399 -> 0.384 ms
     {64, 48, 16, 16, 64, 333, 222, 1, 0, 1, 1},     // up2 (transposed): 0.139 -> 0.113 ms
     {80, 64, 8, 8, 32, 333, 222, 1, 0, 1, 1},       // up3 (transposed): 0.034 -> 0.031 ms
@@ -939,6 +968,11 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     const int hz = KZ == 3 ? 1 : 0, hy = KY == 3 ? 1 : 0;
     const int nphase = tr ? 2 * g->sz : 1;           // (py, pz) phases per CTA; px is a grid dimension
     const int acc_mult = nphase * (src2 ? 2 : 1);
+    // the shortcut of a decoder ResidualUnit reads the conv's own input: its MMAs ride on the centre-tap stages
+    static const bool sc_self_env = !(getenv("VSSEG_TC_SC_SELF") && atoi(getenv("VSSEG_TC_SC_SELF")) == 0);
+    const bool sc_self = src2 && sc_self_env && src2->hi == in->hi && src2->C == in->C && src2->lo_offset == in->lo_offset &&
+                         src2->batch_stride == in->batch_stride;
+    const uint32_t b2_bytes = (uint32_t)(2 * n_cta * 32);
     // flavour
     // line mode: M tile = one z line; the stage holds BY whole input lines (pitch = 128 + 2*hz rows),
     // every tap is an address offset (line, dz) into it.  Needs unit z stride.
@@ -969,7 +1003,7 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
     // N >= 96, while the two A buffers cost TMEM row slots - on this network TS is 5-40 % slower on every layer.
     // Kept as an experiment (default off): VSSEG_TC_TS = 0 off, 1 cost model, 2 forced where possible.
     static const int ts_env = getenv("VSSEG_TC_TS") ? atoi(getenv("VSSEG_TC_TS")) : 0;
-    const bool ts_ok = ts_env != 0 && !tr && !strided && !line && KZ == 1 && LY == 1;
+    const bool ts_ok = ts_env != 0 && !tr && !strided && !line && KZ == 1 && LY == 1 && !sc_self;
     const int sms_ = sm_count();
     // VSSEG_TC_FORCE="XT,YT[,nstage]" (tools/autotune_tiles.py): only that tile is considered; read on every call
     int f_xt = 0, f_yt = 0, f_nst = 0;
@@ -992,7 +1026,7 @@ search:
         if (XT > 1 && XT < xt_min && xt_min <= Xm) continue;
         const int nseg = (Xm + XT - 1) / XT;
         if (XT > 1 && (Xm + nseg - 1) / nseg != XT) continue;   // keep the segments balanced
-        const size_t bstage = round_up((int)((XT > 1 ? KX : 1) * b_bytes), 128);
+        const size_t bstage = round_up((int)((XT > 1 ? KX : 1) * b_bytes + (sc_self ? b2_bytes : 0)), 128);
         const long total_tiles_1 = (long)in->B * nseg * (Zm / LZ) * (tr ? 2 : 1) * n_split;
         for (int YT = 1; YT <= ygroups && YT <= yt_max; ++YT) {
             if (ygroups % YT) continue;
@@ -1060,7 +1094,7 @@ search:
                 main_cyc = nst_main * (mma_cyc > fill_cyc ? mma_cyc : fill_cyc);
             }
             if (src2) {
-                const double f2 = (double)(2 * a_plane + 2 * n_cta * 32) / fill_bpc, m2 = YT * 3.0 * (32 + n_cta / 4.0);
+                const double f2 = sc_self ? 0.0 : (double)(2 * a_plane + 2 * n_cta * 32) / fill_bpc, m2 = YT * 3.0 * (32 + n_cta / 4.0);
                 main_cyc += (double)XT * (src2->C / 16) * (f2 > m2 ? f2 : m2);
             }
             const int units = YT * nphase * (n_cta / 16);
@@ -1101,8 +1135,10 @@ search:
     a.b_off = 2 * a.a_plane;
     a.b_bytes = b_bytes;
     a.b_plane = b_bytes / 2;
-    a.b2_bytes = (uint32_t)(2 * n_cta * 32);
+    a.b2_bytes = b2_bytes;
     a.b2_plane = a.b2_bytes / 2;
+    a.sc_self = sc_self ? 1 : 0;
+    a.b2_off = a.b_off + (uint32_t)((XT > 1 ? KX : 1) * b_bytes);
     a.stage_bytes = (uint32_t)best_stage;
     a.box_tx = box_tx;
     a.lbo_a = (uint32_t)(BY * BZ * 16);
@@ -1154,6 +1190,7 @@ search:
             // the shortcut source is staged with the main box shape: the centre sits at (+hy, +hz)
             if (line) aoff = (uint32_t)(((y + hy) * BZ + hz) * 16);
             else aoff = (uint32_t)((y * LY + hy) * LZ * 16);   // staged unshifted in z (dz2 = 0)
+            if (sc_self && !line) aoff += (uint32_t)hz * box_bytes;   // main stage: the unshifted box is the centre z tap
             for (int pass = 0; pass < 3; ++pass) {
                 TcOp& op = a.ops2[n2++];
                 op.a16 = (uint16_t)(aoff / 16 + (pass == 1 ? a.a_plane / 16 : 0));
@@ -1218,7 +1255,7 @@ static bool make_plan(const vsseg_act8* in, const vsseg_act8* out, const vsseg_c
     memset(&k, 0, sizeof(k));
     key_act(in, k.v); key_act(out, k.v + 7);
     if (src2) key_act(src2, k.v + 14);
-    k.v[21] = src2 ? 1 : 0;
+    k.v[21] = src2 ? (src2->hi == in->hi ? 2 : 1) : 0;   // a shortcut that reads the conv's own input is planned differently
     k.v[22] = g->kx | (g->ky << 4) | (g->kz << 8) | (g->sx << 12) | (g->sy << 16) | (g->sz << 20) | ((g->transposed ? 1 : 0) << 24);
     k.v[23] = n_split;
     if (const char* f = getenv("VSSEG_TC_FORCE")) {   // forced tiles are separate cache entries
@@ -1331,7 +1368,19 @@ static void launch_tc(const TcPlan& P, const CUtensorMap& tmap, const CUtensorMa
         cudaMemsetAsync(dbuf, 0, 256 * 8 * sizeof(unsigned long long), stream);
         a.dbg = dbuf;
     }
-    pick_kernel(a)<<<P.grid, TC_THREADS, P.smem, stream>>>(tmap, tmap2, a);
+    static const bool pdl = getenv("VSSEG_TC_PDL") && atoi(getenv("VSSEG_TC_PDL")) != 0;
+    a.pdl = pdl && !debug ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P.grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = P.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = a.pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, pick_kernel(a), tmap, tmap2, a);
     if (debug) {
         static unsigned long long h[256 * 8];
         cudaStreamSynchronize(stream);

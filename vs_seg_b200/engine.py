@@ -171,7 +171,7 @@ class UNetEvalPlan:
                  strides=((2, 2, 1), (2, 2, 1), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
                  kernel_sizes=((3, 3, 1), (3, 3, 1), (3, 3, 3), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
                  sample_kernel_sizes=((3, 3, 1), (3, 3, 1), (3, 3, 3), (3, 3, 3), (3, 3, 3)),
-                 in_channels=1, out_channels=2, tensor_cores=None):
+                 in_channels=1, out_channels=2, tensor_cores=None, atomic_out=False):
         self.lib = _lib.load()
         self.use_tc = tc_enabled() if tensor_cores is None else bool(tensor_cores)
         self.device = torch.device(device)
@@ -212,6 +212,9 @@ class UNetEvalPlan:
         self.sw_weight = C.c_void_p(None)
         self.atomic_blend = C.c_int32(0)   # set per run(): blend with atomics (several writers of one accumulator)
         self._has_plain_blend = False      # a blending launch that cannot use atomics is part of the plan
+        # the caller always blends with atomics (multi-GPU peer accumulator): the gate+logits launch then takes every
+        # window of the group at once (2048 CTAs instead of 8 x 256 on 296 slots: 0.71 -> 0.55 ms per group of 8)
+        self.atomic_out = bool(atomic_out)
         self._build()
 
     # -- helpers ------------------------------------------------------------------------
@@ -563,7 +566,7 @@ class UNetEvalPlan:
         # ---- fine levels of the decoder, window by window (VSSEG_SW_ATOMIC=1: the fused gate+logits launch takes all
         # windows at once and blends with atomics)
         if (split0 and self.B <= 16 and self._gate_logits_ok(cat[0], self.kernel_sizes[0])
-                and os.environ.get("VSSEG_SW_ATOMIC", "0") == "1"):
+                and (self.atomic_out or os.environ.get("VSSEG_SW_ATOMIC", "0") == "1")):
             decoder(0, "out")
             windows = []
         for bs in windows:
@@ -596,6 +599,8 @@ class UNetEvalPlan:
         self.sw_weight.value = sw_weight_ptr
         if atomic and self._has_plain_blend:
             raise _lib.NativeLibraryError("this plan blends with a launch that has no atomic mode")
+        if self.atomic_out and not atomic and sw_weight_ptr:
+            raise ValueError("run(): a plan built with atomic_out blends with atomics only")
         self.atomic_blend.value = 1 if atomic else 0
 
     def run(self, src, dst, sw_weight_ptr: int | None = None, stream=None, count=True, atomic=False):
@@ -660,7 +665,7 @@ def conv_block_ncdhw(x, sd, kernel_size, stride, transposed, norm, act, residual
     sd holds conv.weight / conv.bias (/ norm.* / act.weight).  Channels are zero-padded to the
     act8 granularity (8 in, 16 out) so any channel count works; pack and unpack are native kernels.
     shortcut = (x_src NCDHW, weight [Cout,Csrc,1,1,1], bias [Cout]) fuses a 1x1x1 shortcut conv as a
-    second accumulator (tensor-core path only).  require_tc raises if the tcgen05 path does not cover
+    second accumulator (tensor-core path only); x_src may be `x` itself (decoder units).  require_tc raises if the tcgen05 path does not cover
     the shape (used by the tests to prove which kernel ran).
     """
     lib = _lib.load()
@@ -701,8 +706,11 @@ def conv_block_ncdhw(x, sd, kernel_size, stride, transposed, norm, act, residual
     sc_v = None
     if shortcut is not None:
         xs, ws, bs = shortcut
-        sbuf = Act8Buffer(B, xs.shape[1], *xs.shape[2:], x.device).from_ncdhw(xs.float())
-        sc_v = sbuf.view()
+        if xs is x:   # a decoder unit: the shortcut reads the conv's own input (no shortcut stages in the kernel)
+            sc_v = src.view()
+        else:
+            sbuf = Act8Buffer(B, xs.shape[1], *xs.shape[2:], x.device).from_ncdhw(xs.float())
+            sc_v = sbuf.view()
     if tc_enabled() and cin8 == cin and cin % 16 == 0:
         ns = lib.vsseg_conv3d_tc_suggest_split(C.byref(sv), C.byref(dv), C.byref(g),
                                                C.byref(sc_v) if sc_v is not None else None)

@@ -184,7 +184,8 @@ class _Program:
                 if len(grp) == 1:
                     call = (model.eval_plan(roi_size, batch=1, device=dev, slot=slot), srcs[0], dsts[0])
                 else:
-                    call = (model.eval_plan(roi_size, batch=len(grp), device=dev, window_levels=levels, slot=slot), srcs, dsts)
+                    call = (model.eval_plan(roi_size, batch=len(grp), device=dev, window_levels=levels, slot=slot,
+                                            atomic_out=self.peer), srcs, dsts)
                 idx.append(len(self.calls))
                 self.calls.append(call)
             self.phases.append(idx)
