@@ -1,4 +1,5 @@
 #!/bin/bash
+# A/B on one B200: programmatic dependent launch of the tensor-core conv kernels (VSSEG_TC_PDL): parity tests, group profile, bench
 O=gpurun_out; mkdir -p $O
 VSSEG_TC_PDL=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q --no-header -rf -k "tcgen05 or unet_eval or window_group or sliding_window or captured or batch_first or two_stream" > $O/e_tests_pdl.log 2>&1; tail -5 $O/e_tests_pdl.log
 for p in 0 1 0 1; do

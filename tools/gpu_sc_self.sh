@@ -1,4 +1,5 @@
 #!/bin/bash
+# A/B on one B200: shortcut MMAs on the centre-tap stages (VSSEG_TC_SC_SELF) vs separate shortcut stages, tile sweep of the decoder units
 O=gpurun_out; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q --no-header -rf -k "tcgen05 or unet_eval or window_group or sliding_window or captured or batch_first" > $O/d_tests.log 2>&1; tail -6 $O/d_tests.log
 run() { local n=$1; shift

@@ -1,4 +1,5 @@
 #!/bin/bash
+# One B200: whole GPU suite, then bench A/B of one vs two streams and window groups of 8 vs 16
 O=gpurun_out; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q --no-header -rf > $O/f_tests.log 2>&1; tail -6 $O/f_tests.log
 b() { local n=$1; shift
