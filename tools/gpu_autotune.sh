@@ -1,5 +1,6 @@
 #!/bin/bash
 # One B200: per-layer tile sweep (tools/autotune_tiles.py), atomic multi-window gate+logits launch, gate batch 8.
+# (variant library: tools/build_variant.sh gb8 -DVSSEG_GATE_BATCH=8)
 O=gpurun_out; mkdir -p $O
 run() { local n=$1; shift
   env "$@" PROFILE_GROUP=8 timeout 150 python tools/profile_plan.py $O/b_pp_$n.tsv > /dev/null 2> $O/b_pp_$n.err

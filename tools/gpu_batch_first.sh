@@ -1,6 +1,7 @@
 #!/bin/bash
 # A/B on one B200: first ResidualUnit batched over the windows of a group (VSSEG_SW_BATCH_FIRST=1), fused level-2
 # attention gate (VSSEG_FUSE_GATE=1) with 1 or 4 channel groups loaded ahead (variant library), then a short bench.
+# (the variant libraries come from: tools/build_variant.sh gb1 -DVSSEG_GATE_BATCH=1 / gb4 -DVSSEG_GATE_BATCH=4; at the time the in-tree default was 1)
 O=gpurun_out; mkdir -p $O
 timeout 200 python -m pytest tests/test_gpu_round2.py -m gpu -q --no-header -rf -k "batch_first or window_group_plan" > $O/a_tests.log 2>&1; tail -4 $O/a_tests.log
 run() { # name, env...

@@ -1489,11 +1489,11 @@ int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const 
     int n = snprintf(buf, buflen,
                      "grid=%u smem=%zu nstage=%d stage_bytes=%u line_mode=%d LZ=%d LY=%d YL=%d BY=%d pitch=%d nbox=%d "
                      "box=[%u,%u,%u,%u,%u] estr=[%u,%u] box_tx=%u a_plane=%u b_off=%u b_bytes=%u lbo_a=%u lbo_b=%u nacc=%d "
-                     "n_cta=%d tmem_cols=%u nchunk=%d nj=%d nchunk2=%d nop=%d nop2=%d ntx=%d nty=%d ntz=%d nsel=%d XT=%d slots=%d ts=%d ops:",
+                     "n_cta=%d tmem_cols=%u nchunk=%d nj=%d nchunk2=%d nop=%d nop2=%d ntx=%d nty=%d ntz=%d nsel=%d XT=%d slots=%d ts=%d sc_self=%d ops:",
                      P.grid, P.smem, a.nstage, a.stage_bytes, a.line_mode, a.LZ, a.LY, a.YL, a.BY, a.pitch, a.nbox, P.box[0],
                      P.box[1], P.box[2], P.box[3], P.box[4], P.estr[1], P.estr[2], a.box_tx, a.a_plane, a.b_off, a.b_bytes,
                      a.lbo_a, a.lbo_b, a.nacc, a.n_cta, a.tmem_cols, a.nchunk, a.nj, a.nchunk2, a.nop, a.nop2, a.ntx, a.nty,
-                     a.ntz, a.nsel, a.XT, a.nbuf, a.ts_mode);
+                     a.ntz, a.nsel, a.XT, a.nbuf, a.ts_mode, a.sc_self);
     for (int i = 0; i < a.nop && n < buflen - 40; ++i)
         n += snprintf(buf + n, buflen - n, " (a%u b%u c%u n%u)", a.ops[i].a16, a.ops[i].b16, a.ops[i].col, a.ops[i].n8 * 8);
     return 0;
