@@ -1019,7 +1019,13 @@ static bool make_plan_uncached(const vsseg_act8* in, const vsseg_act8* out, cons
                 f_xt = h.xt; f_yt = h.yt; hinted = true;
             }
     }
-search:
+    // two attempts at most: with the hinted tile, and - when that tile does not fit this variant of the layer -
+    // with the cost model alone
+    for (int attempt = 0; attempt < 2 && !best; ++attempt) {
+    if (attempt == 1) {
+        if (!hinted) break;
+        f_xt = f_yt = 0;
+    }
     for (int ts = 0; ts <= (ts_ok ? 1 : 0); ++ts)
     for (int XT = 1; XT <= (xt_ok ? (xt_max < Xm ? xt_max : Xm) : 1); ++XT) {
         if (f_xt && XT != f_xt) continue;
@@ -1111,10 +1117,6 @@ search:
             }
         }
     }
-    if (!best && hinted) {   // the hinted tile does not fit this variant of the layer: let the cost model choose
-        hinted = false;
-        f_xt = f_yt = 0;
-        goto search;
     }
     if (!best) return false;
     const int YT = best, XT = best_xt;
