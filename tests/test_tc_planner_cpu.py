@@ -29,10 +29,14 @@ def _describe(B, cin, cout, dims, k, s=(1, 1, 1), tr=False, sc=None, sc_ptr=4096
     ns = lib.vsseg_conv3d_tc_suggest_split(C.byref(a), C.byref(o), C.byref(g), scp)
     if ns <= 0:
         return 0, {}
-    buf = C.create_string_buffer(16384)
-    assert lib.vsseg_conv3d_tc_describe(C.byref(a), C.byref(o), C.byref(g), ns, scp, buf, 16384) == 0
-    head = buf.value.decode().split(" ops:")[0]
-    return ns, {k_: v for k_, v in re.findall(r"(\w+)=(\S+)", head)}
+    buf = C.create_string_buffer(65536)
+    assert lib.vsseg_conv3d_tc_describe(C.byref(a), C.byref(o), C.byref(g), ns, scp, buf, 65536) == 0
+    head, _, ops = buf.value.decode().partition(" ops:")
+    d = {k_: v for k_, v in re.findall(r"(\w+)=(\S+)", head)}
+    main, _, sc_ops = ops.partition(" ops2:")
+    op = lambda t: [tuple(int(v) for v in m) for m in re.findall(r"\(a(\d+) b(\d+) c(\d+) n(\d+)\)", t)]  # noqa: E731
+    d["ops"], d["ops2"] = op(main), op(sc_ops)
+    return ns, d
 
 
 def _layers(patch):
@@ -66,6 +70,15 @@ def test_every_conv_of_the_network_has_a_tensor_core_plan(patch, B):
         assert int(d["tmem_cols"]) <= 512 and int(d["smem"]) <= 227 * 1024 and int(d["nstage"]) >= 2, (name, d)
         assert int(d["sc_self"]) == (1 if same else 0), (name, d)
         assert int(d["nop2"]) == (3 * int(d["YL"]) // int(d["LY"]) if sc else 0), (name, d)
+        assert len(d["ops"]) == int(d["nop"]) and len(d["ops2"]) == int(d["nop2"])
+        if same:
+            # the shortcut's A views are views the conv itself reads from the same stage (its centre tap), one per
+            # line group, hi*hi / lo*hi / hi*lo like the main products, into accumulator columns y * n_cta
+            views = {a_ for a_, _, _, _ in d["ops"]}
+            n_cta = int(d["n_cta"])
+            for i, (a_, b_, c_, n_) in enumerate(d["ops2"]):
+                assert a_ in views and n_ == n_cta and c_ == (i // 3) * n_cta, (name, i, d["ops2"])
+            assert [b_ for _, b_, _, _ in d["ops2"][:3]] == [0, 0, n_cta * 2], (name, d["ops2"][:3])
 
 
 def test_measured_tile_hints_apply_to_window_groups_only():

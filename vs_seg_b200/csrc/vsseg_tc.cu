@@ -1498,6 +1498,9 @@ int vsseg_conv3d_tc_describe(const vsseg_act8* in, const vsseg_act8* out, const 
                      a.ntz, a.nsel, a.XT, a.nbuf, a.ts_mode, a.sc_self);
     for (int i = 0; i < a.nop && n < buflen - 40; ++i)
         n += snprintf(buf + n, buflen - n, " (a%u b%u c%u n%u)", a.ops[i].a16, a.ops[i].b16, a.ops[i].col, a.ops[i].n8 * 8);
+    if (a.nop2 && n < buflen - 40) n += snprintf(buf + n, buflen - n, " ops2:");   // the fused shortcut's products
+    for (int i = 0; i < a.nop2 && n < buflen - 40; ++i)
+        n += snprintf(buf + n, buflen - n, " (a%u b%u c%u n%u)", a.ops2[i].a16, a.ops2[i].b16, a.ops2[i].col, a.ops2[i].n8 * 8);
     return 0;
 }
 
