@@ -129,3 +129,33 @@ def test_oracle_blend_matches_product_generic_path_and_padding():
         ref_c = sw_oracle.sliding_window_inference(x, roi, 1, predictor, mode="constant")
         got_c = sw.sliding_window_inference(x, roi, 1, predictor, mode="constant")
         assert torch.allclose(got_c, ref_c, rtol=1e-5, atol=1e-6)
+
+
+def test_two_stream_phases_pair_only_groups_with_disjoint_destinations():
+    """The sliding-window program runs two window groups at a time on two streams with a plain (non-atomic) blend
+    (vs_seg_b200/sliding_window.py: _Program._pair_groups): the two groups of a phase must never touch the same
+    accumulator voxel, every group runs exactly once, and unpaired groups stay alone."""
+    import numpy as np
+    for image, roi, group, batch in (((384, 384, 160), (128, 128, 128), 8, 1), ((448, 448, 80), (384, 384, 64), 2, 1),
+                                     ((96, 144, 24), (64, 64, 16), 5, 2), ((160, 64, 16), (64, 64, 16), 1, 1),
+                                     ((128, 128, 64), (128, 128, 32), 3, 1)):
+        starts = sw.window_starts(image, roi, 0.25)
+        jobs = [(b, s) for b in range(batch) for s in starts]
+        groups = [jobs[g0:g0 + group] for g0 in range(0, len(jobs), group)]
+        phases = sw._Program._pair_groups(groups, roi)
+        assert sorted(i for ph in phases for i in ph) == list(range(len(groups)))
+        assert all(1 <= len(ph) <= 2 for ph in phases)
+        for ph in phases:
+            if len(ph) < 2:
+                continue
+            marks = []
+            for gi in ph:
+                m = np.zeros((batch,) + tuple(image), dtype=bool)
+                for b, s in groups[gi]:
+                    m[b, s[0]:s[0] + roi[0], s[1]:s[1] + roi[1], s[2]:s[2] + roi[2]] = True
+                marks.append(m)
+            assert not (marks[0] & marks[1]).any(), (image, roi, ph)
+    # the benchmark geometry pairs its four x slabs two by two
+    starts = sw.window_starts((384, 384, 160), (128, 128, 128), 0.25)
+    groups = [[(0, s) for s in starts[g0:g0 + 8]] for g0 in range(0, 32, 8)]
+    assert sw._Program._pair_groups(groups, (128, 128, 128)) == [[0, 2], [1, 3]]
