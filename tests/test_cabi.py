@@ -55,3 +55,24 @@ def test_inconsistent_window_set_is_rejected_without_gpu():
     views[1].sy = 8
     att = lib.Act8(4096, 2 * 8 * n, 8 * n, 2, 8, 8, 8, 8)
     assert h.vsseg_att_gate(C.byref(att), views, C.byref(att), None) == 100001   # plain views only
+
+
+def test_product_path_fails_loudly_without_the_library_or_a_gpu(tmp_path):
+    """No CPU or eager fallback behind the native path: a missing library and a CPU device both raise."""
+    import subprocess
+    import sys
+
+    import pytest
+    env = dict(os.environ, VSSEG_LIB_PATH=str(tmp_path / "missing.so"))
+    code = ("from vs_seg_b200 import lib\n"
+            "try:\n    lib.load()\nexcept lib.NativeLibraryError as e:\n    print('RAISED', e)\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env, timeout=300)
+    assert "RAISED" in out.stdout and "no CPU fallback" in out.stdout, out.stdout + out.stderr
+    from oracle import unet_oracle
+    from vs_seg_b200.engine import UNetEvalPlan, conv_block_ncdhw
+    import torch
+    with pytest.raises(lib.NativeLibraryError):
+        UNetEvalPlan(unet_oracle.seeded_state_dict(0), (64, 64, 16), device="cpu")
+    with pytest.raises(lib.NativeLibraryError):
+        conv_block_ncdhw(torch.zeros(1, 16, 4, 4, 8), {"conv.weight": torch.zeros(16, 16, 3, 3, 1)}, (3, 3, 1), (1, 1, 1),
+                         False, False, "none")
