@@ -76,3 +76,17 @@ def test_product_path_fails_loudly_without_the_library_or_a_gpu(tmp_path):
     with pytest.raises(lib.NativeLibraryError):
         conv_block_ncdhw(torch.zeros(1, 16, 4, 4, 8), {"conv.weight": torch.zeros(16, 16, 3, 3, 1)}, (3, 3, 1), (1, 1, 1),
                          False, False, "none")
+
+
+def test_header_is_plain_c():
+    """include/vsseg_b200.h is the C-ABI contract: it must compile as C99 (plain pointers and sizes, no C++/torch types)."""
+    import shutil
+    import subprocess
+
+    import pytest
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc on this box")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", os.path.join(ROOT, "include", "vsseg_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
